@@ -1,0 +1,92 @@
+"""MeshGaussianModel -- the attribute surface renderer/*/__init__.py reads from a `pc`, backed by the fused ops.
+
+Mirrors games/mesh_splatting/scene/gaussian_mesh_model.py (GaussianMeshModel) + the getters of
+scene/gaussian_model.py:95-122 closely enough that the reference's `render(viewpoint_camera, pc, pipe, bg)`
+(renderer/gaussian_renderer/__init__.py:25) and its animated variant run on it unchanged.  It exists so that
+bench.py / tests do not need /root/reference at run time; a reference GaussianMeshModel instance can instead be
+patched in place with expansion.patch_mesh_model().
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import expansion
+from .scenes import MeshGaussianParams
+
+
+class MeshGaussianModel:
+    def __init__(self, sh_degree: int = 3):
+        self.active_sh_degree = 0
+        self.max_sh_degree = sh_degree
+        self.eps_s0 = expansion.EPS_S0
+        self.vertices = self.faces = self._alpha = self._scale = None
+        self._features_dc = self._features_rest = self._opacity = None
+        self.alpha = self.triangles = self._xyz = self._scaling = self._rotation = None
+        self.optimizer = None
+
+    @classmethod
+    def from_params(cls, p: MeshGaussianParams, device="cuda", sh_degree: int = 3, active_sh_degree: int = 3):
+        m = cls(sh_degree)
+        m.active_sh_degree = active_sh_degree
+        m.faces = p.faces.to(device)
+        for k in ("vertices", "_alpha", "_scale", "_features_dc", "_features_rest", "_opacity"):
+            setattr(m, k, nn.Parameter(getattr(p, k).to(device).float().contiguous().requires_grad_(True)))
+        m.update_alpha()
+        m.prepare_scaling_rot()
+        return m
+
+    # -- the two hooks train.py:154-157 calls every step
+    def update_alpha(self):
+        self.alpha, self.triangles, self._xyz = expansion.update_alpha_op(self.vertices, self.faces, self._alpha)
+
+    def prepare_scaling_rot(self):
+        self._scaling, self._rotation = expansion.prepare_scaling_rot_op(self.triangles, self._scale,
+                                                                         self._alpha.shape[1], self.eps_s0)
+
+    def expand_fused(self, activated: bool = True):
+        """Fast path: one launch for E1-E4; returns (xyz, scaling, rotation) and refreshes alpha/triangles."""
+        xyz, sc, rot, self.alpha, self.triangles = expansion.expand(self.vertices, self.faces, self._alpha, self._scale,
+                                                                    self.eps_s0, activated)
+        if not activated:
+            self._xyz, self._scaling, self._rotation = xyz, sc, rot
+        return xyz, sc, rot
+
+    # -- getters (scene/gaussian_model.py:95-118)
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    @property
+    def get_scaling(self):
+        return torch.exp(self._scaling)
+
+    @property
+    def get_rotation(self):
+        return torch.nn.functional.normalize(self._rotation)
+
+    @property
+    def get_opacity(self):
+        return torch.sigmoid(self._opacity)
+
+    @property
+    def get_features(self):
+        return torch.cat((self._features_dc, self._features_rest), dim=1)
+
+    def oneupSHdegree(self):
+        if self.active_sh_degree < self.max_sh_degree:
+            self.active_sh_degree += 1
+
+    def parameters(self):
+        return [self.vertices, self._alpha, self._features_dc, self._features_rest, self._opacity, self._scale]
+
+    def training_setup(self, vertices_lr=0.0, alpha_lr=0.001, feature_lr=0.0025, opacity_lr=0.05, scaling_lr=0.005):
+        """Adam groups of gaussian_mesh_model.py:171-183 (lrs: arguments_games/__init__.py:17-30)."""
+        groups = [{"params": [self.vertices], "lr": vertices_lr, "name": "vertices"},
+                  {"params": [self._alpha], "lr": alpha_lr, "name": "alpha"},
+                  {"params": [self._features_dc], "lr": feature_lr, "name": "f_dc"},
+                  {"params": [self._features_rest], "lr": feature_lr / 20.0, "name": "f_rest"},
+                  {"params": [self._opacity], "lr": opacity_lr, "name": "opacity"},
+                  {"params": [self._scale], "lr": scaling_lr, "name": "scaling"}]
+        self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        return self.optimizer

@@ -1,0 +1,262 @@
+"""`diff_gaussian_rasterization`-compatible front end over libgms_b200.so.
+
+Mirrors the Python shim of the stock extension ([upstream] diff_gaussian_rasterization/__init__.py of
+graphdeco-inria/diff-gaussian-rasterization) with the API generation the reference's call sites use
+(renderer/gaussian_renderer/__init__.py:43-57, 94-102): 13-field `GaussianRasterizationSettings` (incl.
+`antialiasing`; a 12-field construction still works, antialiasing defaults to False) and a forward that returns
+`(color [3,H,W], radii [P] int32, invdepth [1,H,W])`.
+
+Differences that are observable only as speed: launches go to PyTorch's CURRENT stream (the stock uses the legacy
+default stream), scratch memory comes from the PyTorch caching allocator through the C-ABI callback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    antialiasing: bool = False
+
+
+def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
+    if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+def _opt(t: Optional[torch.Tensor]):
+    """None / empty tensor -> None (the stock shim passes torch.Tensor([]) for absent inputs)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+KEEP_DEBUG = False      # tests set this to True to keep the last forward's scratch reachable
+last_debug = None
+
+
+class _Scratch:
+    """Serves the three scratch regions from torch uint8 tensors and keeps them alive for backward."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+        self.cb = _lib.ALLOC_FN(self._alloc)
+
+    def _alloc(self, user, which, nbytes):
+        try:
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        except Exception:
+            return 0
+        self.bufs[int(which)] = t
+        return t.data_ptr()
+
+
+def _settings_struct(rs: GaussianRasterizationSettings, device, keep: list) -> _lib.RasterSettings:
+    s = _lib.RasterSettings()
+    s.image_height, s.image_width = int(rs.image_height), int(rs.image_width)
+    s.tanfovx, s.tanfovy = float(rs.tanfovx), float(rs.tanfovy)
+    s.scale_modifier = float(rs.scale_modifier)
+    s.sh_degree = int(rs.sh_degree)
+    s.prefiltered, s.debug, s.antialiasing = int(bool(rs.prefiltered)), int(bool(rs.debug)), int(bool(rs.antialiasing))
+    bg, vm, pm, cp = (_dev_f32(rs.bg, device), _dev_f32(rs.viewmatrix, device), _dev_f32(rs.projmatrix, device),
+                      _dev_f32(rs.campos, device))
+    keep += [bg, vm, pm, cp]
+    s.bg, s.viewmatrix, s.projmatrix, s.campos = bg.data_ptr(), vm.data_ptr(), pm.data_ptr(), cp.data_ptr()
+    return s
+
+
+def _inputs_struct(P, M, means3D, opacities, shs, colors, scales, rots, cov) -> _lib.RasterInputs:
+    i = _lib.RasterInputs()
+    i.P, i.M = int(P), int(M)
+    i.means3D, i.opacities = _ptr(means3D), _ptr(opacities)
+    i.shs, i.colors_precomp, i.scales, i.rotations, i.cov3D_precomp = _ptr(shs), _ptr(colors), _ptr(scales), _ptr(rots), _ptr(cov)
+    return i
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+        L = _lib.lib()
+        if not means3D.is_cuda:
+            raise RuntimeError("gms_b200: means3D must be a CUDA tensor (there is no CPU rasterizer in the product path)")
+        device = means3D.device
+        if means3D.dim() != 2 or means3D.shape[1] != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        P = means3D.shape[0]
+        H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+        f = lambda t: None if _opt(t) is None else _dev_f32(t.detach(), device)
+        m3, op = _dev_f32(means3D.detach(), device), f(opacities)
+        shs, col, sc, rot, cov = f(sh), f(colors_precomp), f(scales), f(rotations), f(cov3Ds_precomp)
+        if P > 0 and op is None:
+            raise RuntimeError("opacities must be provided")
+        M = shs.shape[1] if shs is not None else 0
+        keep = []
+        s = _settings_struct(raster_settings, device, keep)
+        i = _inputs_struct(P, M, m3, op, shs, col, sc, rot, cov)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+        radii = torch.empty((P,), dtype=torch.int32, device=device)
+        invdepth = torch.empty((1, H, W), dtype=torch.float32, device=device)
+        o = _lib.RasterOutputs(color.data_ptr(), radii.data_ptr(), invdepth.data_ptr())
+        scratch = _Scratch(device)
+        saved = _lib.RasterSaved()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            rc = L.gms_rasterize_forward(C.byref(s), C.byref(i), C.byref(o), scratch.cb, None, C.byref(saved), stream)
+        if rc != 0 and raster_settings.debug:
+            try:
+                torch.save(tuple(t.cpu() if isinstance(t, torch.Tensor) else t for t in
+                                 (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)), "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+            except Exception:
+                pass
+        _lib.check(rc, "gms_rasterize_forward")
+        if KEEP_DEBUG:
+            global last_debug
+            last_debug = dict(scratch=scratch, num_rendered=int(saved.num_rendered), P=P, W=W, H=H, radii=radii)
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = int(saved.num_rendered)
+        ctx.scratch = scratch
+        ctx.keep = keep
+        ctx.dims = (P, M)
+        ctx.present = (shs is not None, col is not None, sc is not None, rot is not None, cov is not None)
+        ctx.save_for_backward(m3, op if op is not None else torch.empty(0, device=device), shs, col, sc, rot, cov, radii)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, invdepth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii, grad_out_depth):
+        L = _lib.lib()
+        m3, op, shs, col, sc, rot, cov, radii = ctx.saved_tensors
+        device = m3.device
+        P, M = ctx.dims
+        rs = ctx.raster_settings
+        keep = []
+        s = _settings_struct(rs, device, keep)
+        i = _inputs_struct(P, M, m3, op if op.numel() else None, shs, col, sc, rot, cov)
+        saved = _lib.RasterSaved()
+        b = ctx.scratch.bufs
+        saved.geom = _ptr(b.get(_lib.BUF_GEOM)); saved.binning = _ptr(b.get(_lib.BUF_BINNING)); saved.image = _ptr(b.get(_lib.BUF_IMAGE))
+        saved.num_rendered = ctx.num_rendered
+        gcol = _dev_f32(grad_out_color, device)
+        gdep = None if grad_out_depth is None else _dev_f32(grad_out_depth, device)
+        e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+        g_m3, g_m2, g_op = e(P, 3), e(P, 3), e(P, 1)
+        g_sh = e(P, M, 3) if shs is not None else None
+        g_col = e(P, 3) if col is not None else None
+        g_sc = e(P, 3) if sc is not None else None
+        g_rot = e(P, 4) if rot is not None else None
+        g_cov = e(P, 6) if cov is not None else None
+        gr = _lib.RasterGrads(_ptr(g_m3), _ptr(g_m2), _ptr(g_op), _ptr(g_sh), _ptr(g_col), _ptr(g_sc), _ptr(g_rot), _ptr(g_cov))
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            rc = L.gms_rasterize_backward(C.byref(s), C.byref(i), radii.data_ptr(), C.byref(saved), gcol.data_ptr(),
+                                          _ptr(gdep), C.byref(gr), stream)
+        if rc != 0 and rs.debug:
+            try:
+                torch.save((m3.cpu(), radii.cpu(), gcol.cpu()), "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+            except Exception:
+                pass
+        _lib.check(rc, "gms_rasterize_backward")
+        if P == 0:
+            z = lambda t: None if t is None else torch.zeros_like(t)
+            g_m3, g_m2, g_op, g_sh, g_col, g_sc, g_rot, g_cov = map(z, (g_m3, g_m2, g_op, g_sh, g_col, g_sc, g_rot, g_cov))
+        return g_m3, g_m2, g_sh, g_col, g_op, g_sc, g_rot, g_cov, None
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                     raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            rs = self.raster_settings
+            device = positions.device
+            pos = _dev_f32(positions, device)
+            vm, pm = _dev_f32(rs.viewmatrix, device), _dev_f32(rs.projmatrix, device)
+            present = torch.empty((pos.shape[0],), dtype=torch.bool, device=device)
+            rc = _lib.lib().gms_mark_visible(pos.shape[0], pos.data_ptr(), vm.data_ptr(), pm.data_ptr(),
+                                             present.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+            _lib.check(rc, "gms_mark_visible")
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (_opt(shs) is None and _opt(colors_precomp) is None) or (_opt(shs) is not None and _opt(colors_precomp) is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((_opt(scales) is None or _opt(rotations) is None) and _opt(cov3D_precomp) is None) or \
+                ((_opt(scales) is not None or _opt(rotations) is not None) and _opt(cov3D_precomp) is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs)
+
+
+def forward_debug_state(ctx_scratch: _Scratch, num_rendered: int, P: int, W: int, H: int, radii: torch.Tensor):
+    """Parity-test helper: unpack the library's intermediate buffers into torch tensors (stock layouts)."""
+    L = _lib.lib()
+    device = radii.device
+    saved = _lib.RasterSaved()
+    b = ctx_scratch.bufs
+    saved.geom = _ptr(b.get(_lib.BUF_GEOM)); saved.binning = _ptr(b.get(_lib.BUF_BINNING)); saved.image = _ptr(b.get(_lib.BUF_IMAGE))
+    saved.num_rendered = int(num_rendered)
+    out = {}
+    if P > 0:
+        means2D = torch.zeros(P, 2, device=device); depths = torch.zeros(P, device=device)
+        conic = torch.zeros(P, 4, device=device); rgb = torch.zeros(P, 3, device=device)
+        cl = torch.zeros(P, 3, dtype=torch.uint8, device=device)
+        rc = L.gms_debug_unpack(C.byref(saved), P, radii.data_ptr(), means2D.data_ptr(), depths.data_ptr(), conic.data_ptr(),
+                                rgb.data_ptr(), cl.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "gms_debug_unpack")
+        out.update(means2D=means2D, depths=depths, conic_opacity=conic, rgb=rgb, clamped=cl)
+    v = _lib.DebugViews()
+    _lib.check(L.gms_debug_get_views(C.byref(saved), P, W, H, C.byref(v)), "gms_debug_get_views")
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+
+    def view(ptr, n, dtype):
+        if not ptr or n == 0:
+            return torch.zeros(0, dtype=dtype, device=device)
+        nbytes = n * torch.empty(0, dtype=dtype).element_size()
+        for t in b.values():   # locate the owning scratch tensor and slice it
+            base = t.data_ptr()
+            if base <= ptr < base + t.numel():
+                return t[ptr - base: ptr - base + nbytes].view(dtype).clone()
+        raise RuntimeError("debug view outside scratch")
+
+    if P > 0:
+        out["cov3D"] = view(v.cov3D, 6 * P, torch.float32).view(P, 6)
+        out["tiles_touched"] = view(v.tiles_touched, P, torch.int32)
+    out["point_list"] = view(v.point_list, int(num_rendered), torch.int32)
+    out["tile_keys"] = view(v.tile_keys, int(num_rendered), torch.int32)
+    out["ranges"] = view(v.ranges, 2 * T, torch.int32).view(T, 2)
+    out["final_T"] = view(v.final_T, W * H, torch.float32).view(H, W)
+    out["n_contrib"] = view(v.n_contrib, W * H, torch.int32).view(H, W)
+    return out

@@ -1,0 +1,215 @@
+/*
+ * gms_b200.h -- C ABI of libgms_b200.so, the B200-native (sm_100a) mesh-Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for the ONE hot path of waczjoan/gaussian-mesh-splatting:
+ *   mesh -> Gaussian expansion, preprocess (3D->2D + SH), tile binning/sort, per-tile alpha
+ *   compositing forward and backward.
+ * Plain C: raw DEVICE pointers, sizes, a cudaStream_t passed as void*.  No torch types.
+ * Every function returns 0 on success, a negative GMS_E_* code otherwise; gms_last_error()
+ * returns a human-readable message for the calling thread's last failure.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference; the rasterizer
+ * itself is the un-vendored submodule submodules/diff-gaussian-rasterization, so for it the cited lines
+ * are the reference's CALL SITES and [upstream] names the function of graphdeco-inria/diff-gaussian-rasterization
+ * that the reference's pybind module `diff_gaussian_rasterization._C` exports):
+ *
+ *   gms_rasterize_forward    <- _C.rasterize_gaussians            [upstream rasterize_points.cu: RasterizeGaussiansCUDA]
+ *                               reached from renderer/gaussian_renderer/__init__.py:94-102 (and :104-112, :97-105,
+ *                               :99-107 of the animated / points / flame renderers)
+ *   gms_rasterize_backward   <- _C.rasterize_gaussians_backward   [upstream RasterizeGaussiansBackwardCUDA]
+ *                               reached from loss.backward(), train.py:108
+ *   gms_mark_visible         <- _C.mark_visible                   [upstream markVisible]
+ *   gms_expand_forward       <- GaussianMeshModel.update_alpha + _calc_xyz + prepare_scaling_rot + rot_to_quat_batch
+ *                               games/mesh_splatting/scene/gaussian_mesh_model.py:86-169, utils/general_utils.py:19-96,
+ *                               and the activation getters scene/gaussian_model.py:95-115 (optional fused outputs)
+ *   gms_expand_backward      <- the autograd graph of the above (train.py:108 -> vertices/_alpha/_scale .grad)
+ *
+ * Scratch memory follows the stock extension's ownership model: the CALLER owns every byte.  The library
+ * asks for its three scratch regions (per-Gaussian "geom", per-duplicate "binning", per-pixel "image")
+ * through a callback, exactly like the resize-lambdas the stock _C module hands to CudaRasterizer
+ * [upstream rasterize_points.cu: resizeFunctional]; the Python shim serves them from torch uint8 tensors
+ * and keeps them alive for backward (ctx.save_for_backward in the stock shim).
+ */
+#ifndef GMS_B200_H
+#define GMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMS_OK 0
+#define GMS_E_ARG (-1)        /* bad argument combination (e.g. both shs and colors_precomp) */
+#define GMS_E_CUDA (-2)       /* a CUDA call or launch failed; see gms_last_error() */
+#define GMS_E_ALLOC (-3)      /* the allocation callback returned NULL */
+#define GMS_E_UNSUPPORTED (-4)
+
+#define GMS_BUF_GEOM 0
+#define GMS_BUF_BINNING 1
+#define GMS_BUF_IMAGE 2
+
+/* Scratch allocator: must return a device pointer to at least `bytes` bytes, 256-byte aligned, valid on
+ * `stream` order (a torch.empty(uint8) tensor's data_ptr qualifies), or NULL. */
+typedef void* (*gms_alloc_fn)(void* user, int which, size_t bytes);
+
+/* The 13 fields of GaussianRasterizationSettings (renderer/gaussian_renderer/__init__.py:43-57) plus sizes.
+ * Matrices/vectors stay on the DEVICE (they are CUDA tensors at the call site). */
+typedef struct gms_raster_settings {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    const float* bg;          /* device [3] */
+    float scale_modifier;
+    const float* viewmatrix;  /* device [16], world_view_transform (transposed W2C), scene/cameras.py:54 */
+    const float* projmatrix;  /* device [16], full_proj_transform, scene/cameras.py:56 */
+    int32_t sh_degree;        /* active degree 0..3 */
+    const float* campos;      /* device [3] */
+    int32_t prefiltered;
+    int32_t debug;            /* 1: synchronise + check after every launch (stock --debug behaviour) */
+    int32_t antialiasing;
+} gms_raster_settings;
+
+/* Inputs of GaussianRasterizer.forward (renderer/gaussian_renderer/__init__.py:94-102). Exactly one of
+ * shs / colors_precomp and exactly one of (scales, rotations) / cov3D_precomp must be non-NULL. */
+typedef struct gms_raster_inputs {
+    int32_t P;                   /* number of Gaussians */
+    int32_t M;                   /* SH coefficients stored per Gaussian (16 for degree 3); 0 if no shs */
+    const float* means3D;        /* [P,3] */
+    const float* opacities;      /* [P,1] activated */
+    const float* shs;            /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,3] or NULL */
+    const float* scales;         /* [P,3] activated, or NULL */
+    const float* rotations;      /* [P,4] (w,x,y,z) normalised, or NULL */
+    const float* cov3D_precomp;  /* [P,6] or NULL */
+} gms_raster_inputs;
+
+/* Forward outputs (caller-allocated). */
+typedef struct gms_raster_outputs {
+    float* out_color;     /* [3,H,W] */
+    int32_t* radii;       /* [P] */
+    float* out_invdepth;  /* [1,H,W] */
+} gms_raster_outputs;
+
+/* What forward hands back for backward: scratch base pointers (as returned by the callback) and N. */
+typedef struct gms_raster_saved {
+    void* geom;
+    void* binning;
+    void* image;
+    int64_t num_rendered;   /* N = number of (tile, Gaussian) duplicates */
+    int64_t num_visible;    /* Gaussians with radii > 0 (statistics; may be -1 if not computed) */
+} gms_raster_saved;
+
+/* Gradients produced by backward (caller-allocated; NULL where the corresponding input was NULL). */
+typedef struct gms_raster_grads {
+    float* dL_dmeans3D;       /* [P,3] */
+    float* dL_dmeans2D;       /* [P,3] NDC-scaled screen-space gradient, z = 0 */
+    float* dL_dopacities;     /* [P,1] */
+    float* dL_dshs;           /* [P,M,3] */
+    float* dL_dcolors_precomp;/* [P,3] */
+    float* dL_dscales;        /* [P,3] */
+    float* dL_drotations;     /* [P,4] */
+    float* dL_dcov3D_precomp; /* [P,6] */
+} gms_raster_grads;
+
+/* ---- rasterizer ------------------------------------------------------------------------------- */
+
+/* Bytes of the per-Gaussian and per-pixel scratch regions (binning depends on N and is requested
+ * through the callback once N is known). */
+int gms_scratch_bytes(int32_t P, int32_t W, int32_t H, size_t* geom_bytes, size_t* image_bytes);
+size_t gms_binning_bytes(int64_t num_rendered, int32_t P);
+
+int gms_rasterize_forward(const gms_raster_settings* settings, const gms_raster_inputs* in,
+                          const gms_raster_outputs* out, gms_alloc_fn alloc, void* alloc_user,
+                          gms_raster_saved* saved, void* cuda_stream);
+
+/* dL_dout_invdepth may be NULL (train.py never puts a loss on render_pkg["depth"]). */
+int gms_rasterize_backward(const gms_raster_settings* settings, const gms_raster_inputs* in,
+                           const int32_t* radii, const gms_raster_saved* saved,
+                           const float* dL_dout_color /*[3,H,W]*/, const float* dL_dout_invdepth /*[1,H,W]|NULL*/,
+                           const gms_raster_grads* grads, void* cuda_stream);
+
+int gms_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present /*[P] bool*/, void* cuda_stream);
+
+/* Read-only views into the scratch regions, for parity tests and statistics (device pointers). */
+typedef struct gms_debug_views {
+    const float* means2D;        /* packed records [P,12] floats (see gms_debug_unpack for the stock layouts) */
+    const float* depths;         /* unused (NULL) */
+    const float* cov3D;          /* [P,6] */
+    const float* conic_opacity;  /* unused (NULL) */
+    const float* rgb;            /* unused (NULL) */
+    const uint8_t* clamped;      /* unused (NULL) */
+    const uint32_t* tiles_touched; /* [P] */
+    const uint32_t* point_list;  /* [N] Gaussian index per duplicate, sorted by (tile, depth bits, index) */
+    const uint32_t* tile_keys;   /* [N] tile id per duplicate, sorted */
+    const int32_t* ranges;       /* [T,2] */
+    const float* final_T;        /* [H,W] */
+    const int32_t* n_contrib;    /* [H,W] */
+} gms_debug_views;
+int gms_debug_get_views(const gms_raster_saved* saved, int32_t P, int32_t W, int32_t H, gms_debug_views* views);
+/* The per-Gaussian preprocess results live in packed 48-byte records; this unpacks them into the stock
+ * layouts (caller-allocated device buffers, any may be NULL): means2D [P,2], depths [P],
+ * conic_opacity [P,4], rgb [P,3], clamped [P,3] bytes.  Rows of culled Gaussians are zero. */
+int gms_debug_unpack(const gms_raster_saved* saved, int32_t P, const int32_t* radii, float* means2D, float* depths,
+                     float* conic_opacity, float* rgb, uint8_t* clamped, void* cuda_stream);
+
+/* ---- mesh -> Gaussian expansion --------------------------------------------------------------- */
+
+typedef struct gms_expand_args {
+    int32_t V, F, K;             /* vertices, faces, splats per face (P = F*K) */
+    const float* vertices;       /* [V,3] */
+    const int64_t* faces;        /* [F,3] int64 (torch.long), gaussian_mesh_model.py:74 */
+    const float* triangles_in;   /* [F,3,3] or NULL: animated path passes transformed triangles directly
+                                    (renderer/gaussian_animated_renderer/__init__.py:61-73); then vertices/faces unused */
+    const float* alpha_raw;      /* _alpha [F,K,3] */
+    const float* scale_raw;      /* _scale [P,1] */
+    float eps;                   /* eps_s0 = 1e-8, gaussian_mesh_model.py:43 */
+    /* outputs; any may be NULL */
+    float* alpha;                /* [F,K,3] normalised barycentrics (pc.alpha) */
+    float* triangles;            /* [F,3,3] (pc.triangles) */
+    float* xyz;                  /* [P,3] (pc._xyz) */
+    float* scaling_log;          /* [P,3] (pc._scaling) */
+    float* rotation_raw;         /* [P,4] (pc._rotation) */
+    float* scaling_act;          /* [P,3] = exp(_scaling)        (get_scaling, fused E4) */
+    float* rotation_act;         /* [P,4] = normalize(_rotation) (get_rotation, fused E4) */
+} gms_expand_args;
+
+int gms_expand_forward(const gms_expand_args* a, void* cuda_stream);
+
+typedef struct gms_expand_grads {
+    /* incoming (any may be NULL = zero) */
+    const float* dL_dxyz;          /* [P,3] */
+    const float* dL_dscaling_log;  /* [P,3] */
+    const float* dL_drotation_raw; /* [P,4] */
+    const float* dL_dscaling_act;  /* [P,3] gradient w.r.t. exp(_scaling) */
+    const float* dL_drotation_act; /* [P,4] gradient w.r.t. normalize(_rotation) */
+    /* outgoing */
+    float* dL_dvertices;           /* [V,3] ACCUMULATED with atomics: caller zero-fills; NULL if triangles_in */
+    float* dL_dtriangles;          /* [F,3,3] written (NULL allowed) */
+    float* dL_dalpha_raw;          /* [F,K,3] */
+    float* dL_dscale_raw;          /* [P,1] */
+} gms_expand_grads;
+
+int gms_expand_backward(const gms_expand_args* a, const gms_expand_grads* g, void* cuda_stream);
+
+/* ---- misc ------------------------------------------------------------------------------------- */
+const char* gms_last_error(void);
+const char* gms_version(void);
+/* Number of kernel launches issued by this library since the last call with reset != 0 (bench.py's
+ * "gpu_launches" claim is counted, not guessed). */
+int64_t gms_launch_count(int reset);
+/* Per-kernel device time, measured with CUDA events recorded on the launching stream around every launch made
+ * while option "time_kernels" is 1.  Fills up to max_kernels entries (accumulated ms, launch count, name) and
+ * returns the number of kernel slots. */
+int gms_kernel_times(int reset, int max_kernels, double* ms_out, int64_t* count_out, const char** names_out);
+/* Tuning knobs (round-over-round experiments): "quad_masks", "warp_emit", "time_kernels".
+ * Returns the previous value; unknown keys return -1. */
+int gms_set_option(const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMS_B200_H */

@@ -175,6 +175,19 @@ static inline void cov2d_project(const float* pview, const float* cov6, const fl
     o->c = dot3_fma(M1[0], w0, M1[1], w1, M1[2], w2);
 }
 
+/* Canonical evaluation of  -0.5*(cx*dx*dx + cz*dy*dy) - cy*dx*dy  (Appendix A.2): the FMA-contracted
+ * form of the upstream expression; edge-on flat Gaussians make the three terms cancel, so the op order
+ * is part of the contract (the CUDA kernels replay it bit-for-bit; only exp() may differ by ulps). */
+static inline float quad_power(const float* co, float dx, float dy) {
+    float m1 = co[0] * dx;
+    float m2 = m1 * dx;
+    float m3 = co[2] * dy;
+    float t = fmaf(m3, dy, m2);
+    float h = -0.5f * t;
+    float m4 = co[1] * dx;
+    return fmaf(-m4, dy, h);
+}
+
 static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
@@ -451,7 +464,7 @@ int gmso_composite_forward(const gmso_settings* s, const int32_t* ranges, const 
                     uint32_t g = point_list[j];
                     float dx = means2D[2 * g] - pfx, dy = means2D[2 * g + 1] - pfy;
                     const float* co = conic_opacity + 4 * g;
-                    float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                    float power = quad_power(co, dx, dy);
                     if (power > 0.0f) continue;
                     float alpha = fminf(0.99f, co[3] * expf(power));
                     if (fabsf(alpha - 1.0f / 255.0f) < 4e-6f * (1.0f / 255.0f) + 1e-9f) amb = 1;
@@ -522,7 +535,7 @@ int gmso_composite_backward(const gmso_settings* s, const int32_t* ranges, const
                         uint32_t g = point_list[j];
                         float dx = means2D[2 * g] - pfx, dy = means2D[2 * g + 1] - pfy;
                         const float* co = conic_opacity + 4 * g;
-                        float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                        float power = quad_power(co, dx, dy);
                         if (power > 0.0f) continue;
                         float G = expf(power);
                         float alpha = fminf(0.99f, co[3] * G);

@@ -1,0 +1,94 @@
+"""Run the product (CUDA, through the Python shim -> C ABI) and the oracle on the same inputs."""
+import numpy as np
+import torch
+
+import diff_gaussian_rasterization as dgr
+from gms_b200 import rasterizer
+from oracle import raster
+
+
+def gpu_settings(S: raster.Settings, dev="cuda"):
+    t = lambda a: torch.tensor(np.asarray(a, np.float32), device=dev)
+    return dgr.GaussianRasterizationSettings(
+        image_height=S.image_height, image_width=S.image_width, tanfovx=S.tanfovx, tanfovy=S.tanfovy, bg=t(S.bg),
+        scale_modifier=S.scale_modifier, viewmatrix=t(S.viewmatrix), projmatrix=t(S.projmatrix), sh_degree=S.sh_degree,
+        campos=t(S.campos), prefiltered=False, debug=False, antialiasing=S.antialiasing)
+
+
+def run_gpu(S, inputs, dL_dcolor=None, dL_dinv=None, dev="cuda"):
+    """inputs: dict of CPU tensors (means3D, opacities, shs|colors_precomp, scales+rotations|cov3D_precomp).
+    Returns (color, radii, invdepth, debug-state dict, grads dict or None)."""
+    rasterizer.KEEP_DEBUG = True
+    rs = gpu_settings(S, dev)
+    t = {k: v.to(dev).float().clone().requires_grad_(dL_dcolor is not None) for k, v in inputs.items() if v is not None}
+    P = t["means3D"].shape[0]
+    m2d = torch.zeros(P, 3, device=dev, requires_grad=dL_dcolor is not None)
+    r = dgr.GaussianRasterizer(raster_settings=rs)
+    color, radii, invd = r(means3D=t["means3D"], means2D=m2d, opacities=t["opacities"], shs=t.get("shs"),
+                           colors_precomp=t.get("colors_precomp"), scales=t.get("scales"), rotations=t.get("rotations"),
+                           cov3D_precomp=t.get("cov3D_precomp"))
+    dbg = rasterizer.last_debug
+    state = rasterizer.forward_debug_state(dbg["scratch"], dbg["num_rendered"], P, S.image_width, S.image_height, radii)
+    state["num_rendered"] = dbg["num_rendered"]
+    grads = None
+    if dL_dcolor is not None:
+        loss = (color * torch.tensor(dL_dcolor, device=dev)).sum()
+        if dL_dinv is not None:
+            loss = loss + (invd[0] * torch.tensor(dL_dinv, device=dev)).sum()
+        loss.backward()
+        grads = {k: v.grad.detach().cpu().numpy() for k, v in t.items() if v.grad is not None}
+        grads["means2D"] = m2d.grad.detach().cpu().numpy()
+    torch.cuda.synchronize()
+    return color.detach().cpu().numpy(), radii.cpu().numpy(), invd.detach().cpu().numpy(), \
+        {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in state.items()}, grads
+
+
+def run_oracle(S, inputs, dL_dcolor=None, dL_dinv=None):
+    st = raster.forward(S, inputs["means3D"], inputs["opacities"], shs=inputs.get("shs"),
+                        colors_precomp=inputs.get("colors_precomp"), scales=inputs.get("scales"),
+                        rotations=inputs.get("rotations"), cov3D_precomp=inputs.get("cov3D_precomp"))
+    g = None
+    if dL_dcolor is not None:
+        g = raster.backward(st, dL_dcolor, dL_dinv)
+    return st, g
+
+
+def assert_forward_parity(st, color, radii, invd, state, tol=1e-5):
+    """Bit-exact indices, <= tol per pixel (threshold-ambiguous pixels get a bounded looser check)."""
+    np.testing.assert_array_equal(radii, st.radii)
+    assert state["num_rendered"] == st.N
+    if st.radii.shape[0]:
+        np.testing.assert_array_equal(state["tiles_touched"].astype(np.uint32), st.tiles_touched)
+        vis = st.radii > 0
+        np.testing.assert_array_equal(state["means2D"].view(np.uint32)[vis], st.means2D.view(np.uint32)[vis])
+        np.testing.assert_array_equal(state["depths"].view(np.uint32)[vis], st.depths.view(np.uint32)[vis])
+        np.testing.assert_array_equal(state["conic_opacity"].view(np.uint32)[vis], st.conic_opacity.view(np.uint32)[vis])
+        np.testing.assert_array_equal(state["cov3D"].view(np.uint32)[vis], st.cov3Ds.view(np.uint32)[vis])
+        np.testing.assert_array_equal(state["clamped"][vis], st.clamped[vis])
+        np.testing.assert_allclose(state["rgb"][vis], st.rgb[vis], rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(state["point_list"].astype(np.uint32), st.point_list)
+    np.testing.assert_array_equal(state["tile_keys"].astype(np.uint64), st.keys_sorted >> np.uint64(32))
+    np.testing.assert_array_equal(state["ranges"], st.ranges)
+    ok = st.ambiguous == 0
+    assert ok.mean() > 0.999, f"too many threshold-ambiguous pixels: {1 - ok.mean():.2e}"
+    np.testing.assert_array_equal(state["n_contrib"][ok], st.n_contrib[ok])
+    assert np.abs(color - st.color)[:, ok].max() <= tol, np.abs(color - st.color)[:, ok].max()
+    assert np.abs(invd - st.invdepth)[:, ok].max() <= tol
+    assert np.abs(state["final_T"] - st.final_T)[ok].max() <= tol
+    if not ok.all():   # a flipped 1/255 or 1e-4 decision moves a pixel by at most one splat's contribution
+        assert np.abs(color - st.color)[:, ~ok].max() <= 2e-2
+
+
+def assert_grad_parity(g_gpu, g_ref, tol=2e-4):
+    pairs = [("means3D", "dL_dmeans3D"), ("means2D", "dL_dmeans2D"), ("opacities", "dL_dopacity"), ("shs", "dL_dsh"),
+             ("colors_precomp", "dL_dcolors_precomp"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"),
+             ("cov3D_precomp", "dL_dcov3D")]
+    checked = 0
+    for kg, kr in pairs:
+        if kg in g_gpu and g_ref.get(kr) is not None:
+            a, b = g_gpu[kg].astype(np.float64), np.asarray(g_ref[kr], np.float64).reshape(g_gpu[kg].shape)
+            scale = max(np.abs(b).max(), 1e-20)
+            err = np.abs(a - b).max() / scale
+            assert err <= tol, f"grad {kg}: max err / max |ref| = {err:.3e} > {tol}"
+            checked += 1
+    assert checked >= 5

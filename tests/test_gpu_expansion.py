@@ -1,0 +1,106 @@
+"""-m gpu: fused expansion kernels vs the reference-pinned oracle (oracle/expansion.py) and the golden vectors
+the reference's own Python produced; plus the whole frame (expansion -> rasterizer -> loss -> backward)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gms_b200 import expansion, scenes
+from gms_b200.model import MeshGaussianModel
+from oracle import expansion as oexp
+from helpers import settings_from_camera
+
+pytestmark = pytest.mark.gpu
+
+
+def test_expand_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "expansion_mesh.npz"))
+    dev = "cuda"
+    v = torch.tensor(g["vertices"], device=dev, requires_grad=True)
+    a = torch.tensor(g["_alpha"], device=dev, requires_grad=True)
+    s = torch.tensor(g["_scale"], device=dev, requires_grad=True)
+    f = torch.tensor(g["faces"], device=dev)
+    xyz, sl, rr, alpha, tri = expansion.expand(v, f, a, s, activated=False)
+    np.testing.assert_allclose(alpha.cpu().numpy(), g["alpha"], atol=1e-7)
+    np.testing.assert_array_equal(tri.cpu().numpy(), g["triangles"])
+    np.testing.assert_allclose(xyz.detach().cpu().numpy(), g["xyz"], atol=1e-6)
+    np.testing.assert_allclose(sl.detach().cpu().numpy(), g["_scaling"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(rr.detach().cpu().numpy(), g["_rotation"], atol=1e-6)
+    rot = torch.nn.functional.normalize(rr)
+    loss = (xyz * torch.tensor(g["wx"], device=dev)).sum() + (sl * torch.tensor(g["ws"], device=dev)).sum() + \
+           (rot * torch.tensor(g["wr"], device=dev)).sum()
+    loss.backward()
+    np.testing.assert_allclose(v.grad.cpu().numpy(), g["g_vertices"], rtol=3e-4, atol=3e-4)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), g["g_alpha"], rtol=3e-4, atol=1e-5)
+    np.testing.assert_allclose(s.grad.cpu().numpy(), g["g_scale"], rtol=3e-4, atol=1e-5)
+    # activated outputs
+    x2, sa, ra, _, _ = expansion.expand(v.detach(), f, a.detach(), s.detach(), activated=True)
+    np.testing.assert_allclose(sa.cpu().numpy(), g["get_scaling"], rtol=1e-5)
+    np.testing.assert_allclose(ra.cpu().numpy(), g["get_rotation"], atol=1e-6)
+
+
+@pytest.mark.parametrize("level,K", [(3, 3), (5, 5)])
+def test_two_step_protocol_equals_fused_and_oracle(level, K):
+    """update_alpha() + prepare_scaling_rot() (what train.py:154-157 calls) == one fused launch == oracle autograd."""
+    p = scenes.init_mesh_gaussians(*scenes.icosphere(level), K=K, seed=1)
+    dev = "cuda"
+    m = MeshGaussianModel.from_params(p, dev)
+    P = m._scale.shape[0]
+    gen = torch.Generator().manual_seed(0)
+    wx, ws, wr = torch.randn(P, 3, generator=gen), torch.randn(P, 3, generator=gen), torch.randn(P, 4, generator=gen)
+    loss = (m.get_xyz * wx.to(dev)).sum() + (m._scaling * ws.to(dev)).sum() + (m.get_rotation * wr.to(dev)).sum()
+    loss.backward()
+    g2 = [t.grad.clone() for t in (m.vertices, m._alpha, m._scale)]
+    for t in (m.vertices, m._alpha, m._scale):
+        t.grad = None
+    xyz, sl, rr = m.expand_fused(activated=False)
+    loss = (xyz * wx.to(dev)).sum() + (sl * ws.to(dev)).sum() + (torch.nn.functional.normalize(rr) * wr.to(dev)).sum()
+    loss.backward()
+    g1 = [t.grad.clone() for t in (m.vertices, m._alpha, m._scale)]
+    tv, ta, ts = (x.clone().requires_grad_(True) for x in (p.vertices, p._alpha, p._scale))
+    oxyz, osl, orr, _, _ = oexp.expand(tv, p.faces, ta, ts)
+    (oxyz * wx).sum().add((osl * ws).sum()).add((torch.nn.functional.normalize(orr) * wr).sum()).backward()
+    np.testing.assert_allclose(xyz.detach().cpu().numpy(), oxyz.detach().numpy(), atol=2e-6)
+    np.testing.assert_allclose(sl.detach().cpu().numpy(), osl.detach().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(rr.detach().cpu().numpy(), orr.detach().numpy(), atol=2e-6)
+    for a, b, c in zip(g1, g2, (tv.grad, ta.grad, ts.grad)):
+        sc = c.abs().max().item()
+        assert (a.cpu() - c).abs().max().item() / sc < 1e-3
+        assert (b.cpu() - c).abs().max().item() / sc < 1e-3
+
+
+def test_whole_frame_gradients_reach_mesh_parameters():
+    """expansion -> activations -> rasterizer -> loss -> backward: gradient w.r.t. vertices/_alpha/_scale/features/opacity
+    equals oracle expansion autograd chained with the oracle rasterizer backward."""
+    import diff_gaussian_rasterization as dgr
+    from gpu_helpers import gpu_settings
+    from oracle import raster
+    p = scenes.init_mesh_gaussians(*scenes.icosphere(3), K=3, seed=4)
+    cam = scenes.look_at_camera((2.4, 0.8, 1.0), (0, 0, 0), 256, 192)
+    S = settings_from_camera(cam, bg=(1, 1, 1))
+    dev = "cuda"
+    m = MeshGaussianModel.from_params(p, dev)
+    xyz, sc, rot = m.expand_fused(activated=True)
+    r = dgr.GaussianRasterizer(raster_settings=gpu_settings(S))
+    m2d = torch.zeros_like(xyz, requires_grad=True)
+    color, radii, invd = r(means3D=xyz, means2D=m2d, opacities=m.get_opacity, shs=m.get_features, scales=sc, rotations=rot)
+    dC = np.random.RandomState(3).randn(3, 192, 256).astype(np.float32)
+    (color * torch.tensor(dC, device=dev)).sum().backward()
+    # oracle chain
+    tv, ta, ts, to, tdc, trest = (x.clone().requires_grad_(True) for x in (p.vertices, p._alpha, p._scale, p._opacity, p._features_dc, p._features_rest))
+    oxyz, osl, orr, _, _ = oexp.expand(tv, p.faces, ta, ts)
+    osc, orot, oop, ofe = oexp.activate(osl, orr, to, tdc, trest)
+    st = raster.forward(S, oxyz, oop, shs=ofe.contiguous(), scales=osc, rotations=orot)
+    g = raster.backward(st, dC, None)
+    torch.autograd.backward([oxyz, osc, orot, oop, ofe],
+                            [torch.tensor(g["dL_dmeans3D"]), torch.tensor(g["dL_dscales"]), torch.tensor(g["dL_drotations"]),
+                             torch.tensor(g["dL_dopacity"]), torch.tensor(g["dL_dsh"])])
+    ok = st.ambiguous == 0
+    assert np.abs(color.detach().cpu().numpy() - st.color)[:, ok].max() < 1e-5
+    for name, a, b in [("vertices", m.vertices.grad, tv.grad), ("_alpha", m._alpha.grad, ta.grad), ("_scale", m._scale.grad, ts.grad),
+                       ("_opacity", m._opacity.grad, to.grad), ("_features_dc", m._features_dc.grad, tdc.grad),
+                       ("_features_rest", m._features_rest.grad, trest.grad)]:
+        sc_ = b.abs().max().item() + 1e-20
+        err = (a.cpu() - b).abs().max().item() / sc_
+        assert err < 2e-3, f"{name}: {err:.3e}"
