@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec (fwd+bwd) of the mesh-Gaussian hot path at 1080p / 1M mesh-Gaussians (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (CPU oracle)
+
+A "step" is one training frame of gs_mesh (train.py:89-157 of the reference): fused mesh->Gaussian expansion,
+rasterizer forward, L1+SSIM loss, full backward down to vertices/_alpha/_scale/features/opacity, gradient all-reduce
+(N>1) and the Adam step.  Workload = BASELINE config 3: synthetic closed object, F=200,000 faces x K=5 = 1,000,000
+mesh-Gaussians, 1920x1080, SH degree 3, 16 cameras on two rings.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "gaussian-mesh-splatting_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (faces, K, W, H, n_cameras)
+    "gs_mesh_1M_1080p": (200_000, 5, 1920, 1080, 16),       # BASELINE configs[2] -- the headline
+    "gs_mesh_100k_800": (33_334, 3, 800, 800, 8),           # BASELINE configs[1]
+    "gs_mesh_500k_1080p": (100_000, 5, 1920, 1080, 16),     # BASELINE configs[4] sizes (training step variant)
+    "tiny": (2_000, 3, 320, 240, 4),                        # CI-sized
+}
+ALGO_BYTES = {  # algorithmic bytes per unit, SURVEY.md section 8(d) / DESIGN.md "Roofline accounting"
+    "composite_bwd": dict(N=84, px=24), "composite_fwd": dict(N=44, px=24),
+    "preprocess_fwd": dict(P=311), "preprocess_bwd": dict(P=563),
+    "expand_fwd": dict(P=56, F=60), "expand_bwd": dict(P=56, F=36),
+    "emit_dups": dict(P=28, N=8), "cub_sort_tiles": dict(N=16), "cub_sort_depth": dict(P=16), "tile_ranges": dict(N=4),
+    "cub_scan_tiles": dict(P=12),
+}
+
+
+def build_scene(name, seed=0):
+    from gms_b200 import scenes
+    F, K, W, H, ncam = WORKLOADS[name]
+    verts, faces = scenes.object_mesh(F)
+    params = scenes.init_mesh_gaussians(verts, faces, K, seed=seed, trained_like=True)
+    cams = scenes.ring_cameras(ncam // 2, 3.4, W, H, elevation_deg=15.0) + \
+        scenes.ring_cameras(ncam - ncam // 2, 4.4, W, H, elevation_deg=38.0, phase=0.3)
+    return params, cams, (faces.shape[0], K, W, H)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self._stop_evt, self.proc = gpu_index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm / baseline
+def cpu_reference_frame(params, cam, dims, budget_s, threads=None):
+    """One fwd+bwd frame of the SAME workload with the CPU oracle on a bounded sample: expansion (PyTorch CPU +
+    autograd), preprocess, binning and preprocess-backward on all P Gaussians, compositing fwd+bwd on every
+    `stride`-th tile (extrapolated x stride).  Returns (estimated seconds per full frame, description, cores)."""
+    from oracle import expansion as oexp
+    from oracle import raster
+    from helpers import settings_from_camera
+    F, K, W, H = dims
+    cores = raster.num_threads() if threads is None else threads
+    S = settings_from_camera(cam, bg=(1, 1, 1))
+    t0 = time.perf_counter()
+    tv, ta, ts = (x.clone().requires_grad_(True) for x in (params.vertices, params._alpha, params._scale))
+    xyz, sl, rr, _, _ = oexp.expand(tv, params.faces, ta, ts)
+    sc, rot, op, fe = oexp.activate(sl, rr, params._opacity, params._features_dc, params._features_rest)
+    t_exp_f = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    st = raster.preprocess(S, xyz, op, shs=fe.contiguous(), scales=sc, rotations=rot)
+    raster.bin_tiles(st)
+    t_pre = time.perf_counter() - t0
+    T = st.ranges.shape[0]
+    # calibrate the tile stride on a coarse pass
+    raster.set_tile_stride(64)
+    t0 = time.perf_counter(); raster.composite(st); t_c64 = time.perf_counter() - t0
+    est_full = t_c64 * 64 * 3.5     # bwd ~2.5x fwd
+    stride = int(max(1, min(64, math.ceil(est_full / max(budget_s, 1e-3)))))
+    raster.set_tile_stride(stride)
+    rs = np.random.RandomState(0)
+    dC = (rs.randn(3, H, W) / (W * H)).astype(np.float32)
+    t0 = time.perf_counter(); raster.composite(st); t_cf = time.perf_counter() - t0
+    t0 = time.perf_counter(); g = raster.composite_backward(st, dC, None); t_cb = time.perf_counter() - t0
+    t0 = time.perf_counter(); out = raster.preprocess_backward(st, g); t_pb = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    torch.autograd.backward([xyz, sc, rot], [torch.tensor(out["dL_dmeans3D"]), torch.tensor(out["dL_dscales"]),
+                                              torch.tensor(out["dL_drotations"])])
+    t_exp_b = time.perf_counter() - t0
+    raster.set_tile_stride(1)
+    frame_s = t_exp_f + t_pre + (t_cf + t_cb) * stride + t_pb + t_exp_b
+    desc = (f"1 frame of the same workload (P={F * K}, {W}x{H}, N={st.N}): expansion+preprocess+binning+preprocess-bwd on all "
+            f"Gaussians, compositing fwd+bwd on every {stride}-th of {T} tiles, extrapolated x{stride}; "
+            f"measured {t_exp_f + t_pre + t_cf + t_cb + t_pb + t_exp_b:.1f}s")
+    return frame_s, desc, cores
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the stock CUDA extension is an
+    empty un-vendored submodule and cannot be installed)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    params, cams, dims = build_scene(args.workload)
+    per_step_budget = max(2.0, 150.0 / max(1, args.steps + args.warmup))
+    times = []
+    for s in range(args.warmup + args.steps):
+        fs, desc, cores = cpu_reference_frame(params, cams[s % len(cams)], dims, per_step_budget)
+        if s >= args.warmup:
+            times.append(fs)
+    sec = float(np.mean(times))
+    F, K, W, H = dims
+    line = {"impl": "reference", "metric": "frames/sec (fwd+bwd) @1080p, 1M mesh-Gaussians", "value": 1.0 / sec,
+            "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "P": F * K, "faces": F, "K": K, "width": W, "height": H, "sh_degree": 3},
+            "cpu_baseline": {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": 1.0 / sec, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference arm = CPU oracle port of the reference algorithm (stock diff-gaussian-rasterization source is "
+                    "absent from the reference checkout: empty submodule)"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gs_mesh_1M_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-optimizer", action="store_true", help="exclude the Adam step from the step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from gms_b200 import _lib, rasterizer
+    from gms_b200.model import MeshGaussianModel
+    from gms_b200.trainer import MeshTrainer, render_frame, shard_cameras
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a GPU: the product has no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K_, W_ = args.steps, max(args.warmup, 3)
+
+    params, cams, dims = build_scene(args.workload)
+    F, K, W, H = dims
+    P = F * K
+    model = MeshGaussianModel.from_params(params, dev)
+    bg = torch.ones(3, device=dev)
+    cams_dev = [c.to(dev) for c in cams]
+    # ground truth: the same object with different appearance, rendered once per camera (synthetic data)
+    gt_params = build_scene(args.workload, seed=123)[0]
+    gt_model = MeshGaussianModel.from_params(gt_params, dev)
+    with torch.no_grad():
+        gts = [render_frame(gt_model, c, bg)[0].clamp(0, 1).contiguous() for c in cams_dev]
+    del gt_model
+    gts_host = [g.cpu().pin_memory() for g in gts]
+    cam_host = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center.reshape(-1)]).pin_memory()
+                for c in cams]
+    trainer = MeshTrainer(model, bg, world=world, rank=rank, optimizer_step=not args.no_optimizer)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, first_step):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(first_step + s)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    n_frames = []
+
+    def step_resident(s):
+        ci = shard_cameras(len(cams), s, rank, world)
+        trainer.step(cams_dev[ci], gts[ci])
+        n_frames.append(rasterizer.last_num_rendered)
+
+    cam_buf = torch.empty(35, device=dev)
+    gt_buf = torch.empty(3, H, W, device=dev)
+    from gms_b200.scenes import Camera
+    h2d = gts_host[0].numel() * 4 + 35 * 4
+
+    def step_e2e(s):
+        ci = shard_cameras(len(cams), s, rank, world)
+        gt_buf.copy_(gts_host[ci], non_blocking=True)
+        cam_buf.copy_(cam_host[ci], non_blocking=True)
+        c = cams[ci]
+        cam = Camera(c.image_width, c.image_height, c.FoVx, c.FoVy, cam_buf[:16].view(4, 4), cam_buf[16:32].view(4, 4), cam_buf[32:35])
+        loss = trainer.step(cam, gt_buf)
+        return loss.item()     # device -> host read of the step's result
+
+    for s in range(W_):
+        step_resident(s)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.launch_count(reset=True)
+    n_frames.clear()
+    ms_total = timed(step_resident, K_, W_)
+    launches = _lib.launch_count(reset=True)
+    for s in range(2):
+        step_e2e(s)
+    ms_e2e = timed(step_e2e, K_, W_ + K_)
+    if sampler:
+        sampler.stop()
+    # per-kernel device time (CUDA events on the launching stream, inside the library), separate pass
+    _lib.set_option("time_kernels", 1)
+    _lib.kernel_times(reset=True)
+    barrier()
+    for s in range(min(K_, 10)):
+        step_resident(W_ + 2 * K_ + s)
+    torch.cuda.synchronize()
+    kt = _lib.kernel_times(reset=True)
+    _lib.set_option("time_kernels", 0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms_total / K_
+    value = world * 1000.0 / ms_step
+    e2e_value = world * 1000.0 / (ms_e2e / K_)
+    N_mean = float(np.mean(n_frames)) if n_frames else 0.0
+    units = {"P": P, "F": F, "N": N_mean, "px": W * H}
+    per_kernel = {}
+    for name, (ms, cnt) in kt.items():
+        if cnt:
+            ab = sum(ALGO_BYTES.get(name, {}).get(u, 0) * units[u] for u in units)
+            per_kernel[name] = {"ms": ms / cnt, "launches_per_step": cnt / min(K_, 10), "algo_bytes": ab,
+                                "gbs": (ab / (ms / cnt * 1e-3) / 1e9) if ms > 0 else None}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"] * per_kernel[k]["launches_per_step"]) if per_kernel else None
+    peak, peak_src = measured_peak_gbs()
+    roof = None
+    if dom:
+        a = per_kernel[dom]["gbs"]
+        roof = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": per_kernel[dom]["ms"],
+                "algo_bytes_per_launch": per_kernel[dom]["algo_bytes"],
+                "note": "composite kernels are FP32-issue bound (exp + ~50 flops per pixel x splat), not HBM bound; see DESIGN.md"}
+    frame_bytes = 1014 * P + 96 * F + 172 * N_mean + 48 * W * H
+    line = {"metric": "frames/sec (fwd+bwd) @1080p, 1M mesh-Gaussians", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": K_, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "P": P, "faces": F, "K": K, "width": W, "height": H, "sh_degree": 3,
+                       "cameras": len(cams), "N_mean": N_mean, "optimizer_step": not args.no_optimizer,
+                       "parallelism": f"frame-sharded dp{world}", "l2": "inputs_exceed_l2 (per-step working set > 126 MB)",
+                       "frame_algo_bytes": frame_bytes, "frame_hbm_frac": frame_bytes / (ms_step * 1e-3) / 1e9 / peak},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / K_},
+            "gpu_launches": int(launches), "roofline": roof, "kernels": per_kernel,
+            "clocks": sampler.summary() if sampler else None}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            fs, desc, cores = cpu_reference_frame(params, cams[0], dims, args.cpu_budget)
+            line["cpu_baseline"] = {"value": 1.0 / fs, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

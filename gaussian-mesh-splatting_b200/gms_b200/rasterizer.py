@@ -55,6 +55,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 KEEP_DEBUG = False      # tests set this to True to keep the last forward's scratch reachable
 last_debug = None
+last_num_rendered = 0   # N of the most recent forward (statistics for bench.py)
 
 
 class _Scratch:
@@ -133,6 +134,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             except Exception:
                 pass
         _lib.check(rc, "gms_rasterize_forward")
+        global last_num_rendered
+        last_num_rendered = int(saved.num_rendered)
         if KEEP_DEBUG:
             global last_debug
             last_debug = dict(scratch=scratch, num_rendered=int(saved.num_rendered), P=P, W=W, H=H, radii=radii)
@@ -212,10 +215,10 @@ class GaussianRasterizer(nn.Module):
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None):
         rs = self.raster_settings
-        if (_opt(shs) is None and _opt(colors_precomp) is None) or (_opt(shs) is not None and _opt(colors_precomp) is not None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
-        if ((_opt(scales) is None or _opt(rotations) is None) and _opt(cov3D_precomp) is None) or \
-                ((_opt(scales) is not None or _opt(rotations) is not None) and _opt(cov3D_precomp) is not None):
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs)
 

@@ -64,6 +64,10 @@ static const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570
                                0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                -0.5900435899266435f};
 
+/* Bounded-sample support for the CPU baseline (bench.py): composite only tiles with tile % stride == 0. */
+static int g_tile_stride = 1;
+void gmso_set_tile_stride(int s) { g_tile_stride = s > 0 ? s : 1; }
+
 int gmso_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -452,6 +456,7 @@ int gmso_composite_forward(const gmso_settings* s, const int32_t* ranges, const 
     const int gx = (W + GMSO_BLOCK - 1) / GMSO_BLOCK, gy = (H + GMSO_BLOCK - 1) / GMSO_BLOCK;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int tile = 0; tile < gx * gy; tile++) {
+        if (tile % g_tile_stride) continue;
         int tx0 = (tile % gx) * GMSO_BLOCK, ty0 = (tile / gx) * GMSO_BLOCK;
         int r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
         for (int py = ty0; py < ty0 + GMSO_BLOCK && py < H; py++)
@@ -516,6 +521,7 @@ int gmso_composite_backward(const gmso_settings* s, const int32_t* ranges, const
         double* l_m = (double*)calloc((size_t)P * 10, sizeof(double));
 #pragma omp for schedule(dynamic, 1)
         for (int tile = 0; tile < gx * gy; tile++) {
+            if (tile % g_tile_stride) continue;
             int tx0 = (tile % gx) * GMSO_BLOCK, ty0 = (tile / gx) * GMSO_BLOCK;
             int r0 = ranges[2 * tile];
             for (int py = ty0; py < ty0 + GMSO_BLOCK && py < H; py++)

@@ -64,6 +64,11 @@ def set_num_threads(n: int) -> None:
     lib().gmso_set_num_threads(int(n))
 
 
+def set_tile_stride(stride: int) -> None:
+    """Composite only every `stride`-th tile (bounded CPU-baseline samples); 1 = all tiles."""
+    lib().gmso_set_tile_stride(int(stride))
+
+
 def _p(a: Optional[np.ndarray]):
     if a is None:
         return None
