@@ -38,7 +38,7 @@ ALGO_BYTES = {  # algorithmic bytes per unit, SURVEY.md section 8(d) / DESIGN.md
     "preprocess_fwd": dict(P=311), "preprocess_bwd": dict(P=563),
     "expand_fwd": dict(P=56, F=60), "expand_bwd": dict(P=56, F=36),
     "emit_dups": dict(P=28, N=8), "cub_sort_tiles": dict(N=16), "cub_sort_depth": dict(P=16), "tile_ranges": dict(N=4),
-    "cub_scan_tiles": dict(P=12),
+    "cub_scan_tiles": dict(P=12), "ssim_stats": dict(px=3 * (8 + 12)), "ssim_grad": dict(px=3 * (12 + 8 + 4)), "adam": dict(P=53 * 28 + 0),
 }
 
 
@@ -179,12 +179,14 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gs_mesh_1M_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-optimizer", action="store_true", help="exclude the Adam step from the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-ops", action="store_true",
+                    help="glue ops as the reference orders them (two-step expansion, ATen loss, torch Adam) around our rasterizer")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -208,7 +210,7 @@ def main():
     params, cams, dims = build_scene(args.workload)
     F, K, W, H = dims
     P = F * K
-    model = MeshGaussianModel.from_params(params, dev)
+    model = MeshGaussianModel.from_params(params, dev, packed_features=not args.reference_ops)
     bg = torch.ones(3, device=dev)
     cams_dev = [c.to(dev) for c in cams]
     # ground truth: the same object with different appearance, rendered once per camera (synthetic data)
@@ -220,7 +222,7 @@ def main():
     gts_host = [g.cpu().pin_memory() for g in gts]
     cam_host = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center.reshape(-1)]).pin_memory()
                 for c in cams]
-    trainer = MeshTrainer(model, bg, world=world, rank=rank, optimizer_step=not args.no_optimizer)
+    trainer = MeshTrainer(model, bg, world=world, rank=rank, optimizer_step=not args.no_optimizer, fast=not args.reference_ops)
 
     def barrier():
         if world > 1:
@@ -314,7 +316,7 @@ def main():
             "steps": K_, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "P": P, "faces": F, "K": K, "width": W, "height": H, "sh_degree": 3,
-                       "cameras": len(cams), "N_mean": N_mean, "optimizer_step": not args.no_optimizer,
+                       "cameras": len(cams), "N_mean": N_mean, "optimizer_step": not args.no_optimizer, "glue": "reference-ops" if args.reference_ops else "fused",
                        "parallelism": f"frame-sharded dp{world}", "l2": "inputs_exceed_l2 (per-step working set > 126 MB)",
                        "frame_algo_bytes": frame_bytes, "frame_hbm_frac": frame_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -73,13 +73,26 @@ class ExpandGrads(C.Structure):
                 ("dL_dscale_raw", C.c_void_p)]
 
 
+class LossArgs(C.Structure):
+    _fields_ = [("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("img", C.c_void_p), ("gt", C.c_void_p),
+                ("lambda_dssim", C.c_float), ("dL_dloss", C.c_void_p), ("loss", C.c_void_p), ("dL_dimg", C.c_void_p),
+                ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t)]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("nseg", C.c_int32), ("seg_end", C.c_int64 * 8), ("lr0", C.c_float * 8), ("lr1", C.c_float * 8),
+                ("inner", C.c_int32 * 8), ("period", C.c_int32 * 8), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("step", C.c_int32), ("zero_grad", C.c_int32)]
+
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
 
 # every symbol include/gms_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = ["gms_scratch_bytes", "gms_binning_bytes", "gms_rasterize_forward", "gms_rasterize_backward",
                "gms_mark_visible", "gms_debug_get_views", "gms_debug_unpack", "gms_expand_forward",
                "gms_expand_backward", "gms_last_error", "gms_version", "gms_launch_count", "gms_set_option",
-               "gms_kernel_times"]
+               "gms_kernel_times", "gms_loss_scratch_bytes", "gms_l1_ssim_loss", "gms_adam_step"]
 
 _lib = None
 
@@ -116,6 +129,9 @@ def lib():
     L.gms_expand_forward.argtypes = [C.POINTER(ExpandArgs), C.c_void_p]
     L.gms_expand_backward.argtypes = [C.POINTER(ExpandArgs), C.POINTER(ExpandGrads), C.c_void_p]
     L.gms_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.gms_loss_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    L.gms_l1_ssim_loss.argtypes = [C.POINTER(LossArgs), C.c_void_p]
+    L.gms_adam_step.argtypes = [C.POINTER(AdamArgs), C.c_void_p]
     _lib = L
     return L
 

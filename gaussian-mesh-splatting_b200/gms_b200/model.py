@@ -21,20 +21,37 @@ class MeshGaussianModel:
         self.max_sh_degree = sh_degree
         self.eps_s0 = expansion.EPS_S0
         self.vertices = self.faces = self._alpha = self._scale = None
-        self._features_dc = self._features_rest = self._opacity = None
+        self._features = None
+        self._opacity = None
         self.alpha = self.triangles = self._xyz = self._scaling = self._rotation = None
         self.optimizer = None
 
     @classmethod
-    def from_params(cls, p: MeshGaussianParams, device="cuda", sh_degree: int = 3, active_sh_degree: int = 3):
+    def from_params(cls, p: MeshGaussianParams, device="cuda", sh_degree: int = 3, active_sh_degree: int = 3,
+                    packed_features: bool = False):
+        """packed_features: keep SH coefficients in ONE [P,16,3] parameter (`_features`); `_features_dc` / `_features_rest`
+        become views of it and get_features is zero-copy (the reference's torch.cat re-materialises 192 B/Gaussian
+        every frame, scene/gaussian_model.py:107-111).  Needs FlatAdam for the DC / rest learning rates."""
         m = cls(sh_degree)
         m.active_sh_degree = active_sh_degree
         m.faces = p.faces.to(device)
-        for k in ("vertices", "_alpha", "_scale", "_features_dc", "_features_rest", "_opacity"):
-            setattr(m, k, nn.Parameter(getattr(p, k).to(device).float().contiguous().requires_grad_(True)))
+        mk = lambda t: nn.Parameter(t.to(device).float().contiguous().requires_grad_(True))
+        for k in ("vertices", "_alpha", "_scale", "_opacity"):
+            setattr(m, k, mk(getattr(p, k)))
+        if packed_features:
+            m._features = mk(torch.cat((p._features_dc, p._features_rest), dim=1))
+        else:
+            m._features = None
+            m._features_dc, m._features_rest = mk(p._features_dc), mk(p._features_rest)
         m.update_alpha()
         m.prepare_scaling_rot()
         return m
+
+    def __getattr__(self, name):   # only called when normal lookup fails: packed-mode views
+        if name in ("_features_dc", "_features_rest") and self.__dict__.get("_features") is not None:
+            f = self.__dict__["_features"]
+            return f[:, :1] if name == "_features_dc" else f[:, 1:]
+        raise AttributeError(name)
 
     # -- the two hooks train.py:154-157 calls every step
     def update_alpha(self):
@@ -71,6 +88,8 @@ class MeshGaussianModel:
 
     @property
     def get_features(self):
+        if self._features is not None:
+            return self._features
         return torch.cat((self._features_dc, self._features_rest), dim=1)
 
     def oneupSHdegree(self):
@@ -78,10 +97,14 @@ class MeshGaussianModel:
             self.active_sh_degree += 1
 
     def parameters(self):
+        if self._features is not None:
+            return [self.vertices, self._alpha, self._features, self._opacity, self._scale]
         return [self.vertices, self._alpha, self._features_dc, self._features_rest, self._opacity, self._scale]
 
     def training_setup(self, vertices_lr=0.0, alpha_lr=0.001, feature_lr=0.0025, opacity_lr=0.05, scaling_lr=0.005):
         """Adam groups of gaussian_mesh_model.py:171-183 (lrs: arguments_games/__init__.py:17-30)."""
+        if self._features is not None:
+            raise RuntimeError("packed features need gms_b200.optim.FlatAdam (per-coefficient learning rates)")
         groups = [{"params": [self.vertices], "lr": vertices_lr, "name": "vertices"},
                   {"params": [self._alpha], "lr": alpha_lr, "name": "alpha"},
                   {"params": [self._features_dc], "lr": feature_lr, "name": "f_dc"},

@@ -19,35 +19,15 @@ import torch.distributed as dist
 
 import diff_gaussian_rasterization as dgr
 
-from .losses import training_loss
+from .losses import training_loss, fused_training_loss
 from .model import MeshGaussianModel
+from .optim import FlatAdam, mesh_model_groups
 from .scenes import Camera
 
 
 def shard_cameras(n_cameras: int, step: int, rank: int, world: int) -> int:
     """Camera index rank `rank` renders at `step`: consecutive cameras of the schedule go to consecutive ranks."""
     return (step * world + rank) % n_cameras
-
-
-class FlatGrads:
-    """Points every parameter's .grad into one flat fp32 buffer (single-collective gradient exchange)."""
-
-    def __init__(self, params: Sequence[torch.nn.Parameter]):
-        self.params = list(params)
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-
-    def zero_(self):
-        self.flat.zero_()
-
-    def all_reduce_mean(self, world: int, group=None):
-        if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.mul_(1.0 / world)
 
 
 def render_frame(model: MeshGaussianModel, cam: Camera, bg: torch.Tensor, fused: bool = True, antialiasing: bool = False):
@@ -67,22 +47,49 @@ def render_frame(model: MeshGaussianModel, cam: Camera, bg: torch.Tensor, fused:
 
 
 class MeshTrainer:
+    """fwd + loss + bwd (+ gradient all-reduce) + Adam for one frame per rank.
+
+    fast=True  : fused expansion launch, packed SH features (zero-copy get_features), fused L1+SSIM loss kernels,
+                 FlatAdam (one launch, zeroes the gradient) -- everything on the library's kernels except sigmoid.
+    fast=False : the reference's op sequence (two-step expansion + getters, ATen loss, torch.optim.Adam)."""
+
     def __init__(self, model: MeshGaussianModel, bg: torch.Tensor, lambda_dssim: float = 0.2, world: int = 1,
-                 rank: int = 0, optimizer_step: bool = True, fused_expansion: bool = True):
+                 rank: int = 0, optimizer_step: bool = True, fast: bool = True):
         self.model, self.bg, self.lambda_dssim = model, bg, lambda_dssim
         self.world, self.rank = world, rank
         self.optimizer_step = optimizer_step
-        self.fused = fused_expansion
-        self.opt = model.training_setup() if optimizer_step else None
-        self.grads = FlatGrads(model.parameters())
+        self.fast = fast
+        if fast:
+            self.opt = FlatAdam(mesh_model_groups(model))
+            self.flat_grad = self.opt.flat_grad
+        else:
+            self.opt = model.training_setup()
+            self.flat_grad = None
+
+    def _all_reduce(self):
+        if self.world <= 1:
+            return
+        if self.flat_grad is not None:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            self.flat_grad.mul_(1.0 / self.world)
+        else:
+            for p in self.model.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+                    p.grad.mul_(1.0 / self.world)
 
     def step(self, cam: Camera, gt: torch.Tensor) -> torch.Tensor:
-        """fwd + loss + bwd (+ gradient all-reduce) (+ Adam).  Returns the (device) loss scalar."""
-        self.grads.zero_()
-        image, radii, _ = render_frame(self.model, cam, self.bg, self.fused)
-        loss = training_loss(image, gt, self.lambda_dssim)
+        image, radii, _ = render_frame(self.model, cam, self.bg, fused=self.fast)
+        loss = fused_training_loss(image, gt, self.lambda_dssim) if self.fast else training_loss(image, gt, self.lambda_dssim)
         loss.backward()
-        self.grads.all_reduce_mean(self.world)
-        if self.opt is not None:
+        self._all_reduce()
+        if self.optimizer_step:
             self.opt.step()
+            if not self.fast:
+                self.opt.zero_grad(set_to_none=False)
+        elif self.fast:
+            self.opt.zero_grad()
+        else:
+            for p in self.model.parameters():
+                p.grad = None
         return loss.detach()

@@ -195,6 +195,41 @@ typedef struct gms_expand_grads {
 
 int gms_expand_backward(const gms_expand_args* a, const gms_expand_grads* g, void* cuda_stream);
 
+/* ---- training-step glue on the same stream (the callers either side of the path) ---- */
+
+/* L = (1-lambda)*L1 + lambda*(1-SSIM) and dL/dimg in two launches.  Replaces utils/loss_utils.py:17-64 as used by
+ * train.py:105-108 (5 grouped conv2d forward + 5 backward + ~30 elementwise launches per frame). */
+typedef struct gms_loss_args {
+    int32_t C, H, W;
+    const float* img;        /* [C,H,W] rendered image */
+    const float* gt;         /* [C,H,W] ground truth */
+    float lambda_dssim;      /* 0.2, arguments/__init__.py:86 */
+    const float* dL_dloss;   /* device scalar upstream gradient, or NULL for 1 */
+    float* loss;             /* device [3]: loss, L1 mean, SSIM mean */
+    float* dL_dimg;          /* [C,H,W] or NULL (forward only) */
+    void* scratch;           /* gms_loss_scratch_bytes() bytes */
+    size_t scratch_bytes;
+} gms_loss_args;
+int gms_loss_scratch_bytes(int32_t C, int32_t H, int32_t W, size_t* bytes);
+int gms_l1_ssim_loss(const gms_loss_args* a, void* cuda_stream);
+
+/* torch.optim.Adam(groups, eps=1e-15) of gaussian_mesh_model.py:171-183 (train.py:146-148) over ONE flat fp32
+ * parameter buffer, one launch; consumes and (optionally) zeroes the gradient in the same pass.
+ * Segment i covers flat indices [seg_end[i-1], seg_end[i]); lr = lr0[i], or -- when period[i] > 0 --
+ * lr0[i] where ((index - segment start) / inner[i]) % period[i] == 0 and lr1[i] elsewhere (DC vs rest SH). */
+typedef struct gms_adam_args {
+    int64_t n;
+    float* p; float* g; float* m; float* v;
+    int32_t nseg;
+    int64_t seg_end[8];
+    float lr0[8]; float lr1[8];
+    int32_t inner[8]; int32_t period[8];
+    float beta1, beta2, eps;
+    int32_t step;            /* 1-based step count (bias correction) */
+    int32_t zero_grad;
+} gms_adam_args;
+int gms_adam_step(const gms_adam_args* a, void* cuda_stream);
+
 /* ---- misc ------------------------------------------------------------------------------------- */
 const char* gms_last_error(void);
 const char* gms_version(void);

@@ -13,6 +13,7 @@ What is pinned (everything the reference ships in Python on or beside the hot pa
   sh_colors.npz        eval_sh + 0.5 clamp (utils/sh_utils.py:57-112; renderer/gaussian_renderer/__init__.py:82-87)
   cov3d.npz            build_scaling_rotation / strip_symmetric (utils/general_utils.py:144-190,
                        scene/gaussian_model.py:27-31)  == --compute_cov3D_python
+  loss.npz             l1_loss / ssim / 0.8*L1 + 0.2*(1-SSIM) and its autograd gradient (utils/loss_utils.py:17-64, train.py:105-107)
   camera.npz           getWorld2View2 / getProjectionMatrix / Camera matrix algebra
                        (utils/graphics_utils.py:22-71, scene/cameras.py:54-57), geom_transform_points
 The reference hard-codes device="cuda" in a few helpers; the generator temporarily maps those
@@ -66,6 +67,8 @@ from games.multi_mesh_splatting.scene.gaussian_multi_mesh_model import GaussianM
 from utils.sh_utils import eval_sh  # noqa: E402
 from utils.general_utils import build_scaling_rotation, strip_symmetric, rot_to_quat_batch  # noqa: E402
 from utils.graphics_utils import getWorld2View2, getProjectionMatrix, geom_transform_points  # noqa: E402
+
+from utils.loss_utils import l1_loss as ref_l1, ssim as ref_ssim  # noqa: E402
 
 from gms_b200 import scenes  # noqa: E402
 
@@ -196,8 +199,19 @@ def quat():
     np.savez_compressed(os.path.join(HERE, "rot_to_quat.npz"), R=R.numpy(), quat=out.numpy())
 
 
+def loss():
+    g = torch.Generator().manual_seed(8)
+    a = torch.rand(3, 45, 70, generator=g, requires_grad=True)
+    b = (a.detach() + 0.15 * torch.randn(3, 45, 70, generator=g)).clamp(0, 1)
+    l1 = ref_l1(a, b); ss = ref_ssim(a, b)
+    total = (1.0 - 0.2) * l1 + 0.2 * (1.0 - ss)     # train.py:106-107, lambda_dssim = 0.2
+    total.backward()
+    np.savez_compressed(os.path.join(HERE, "loss.npz"), img=a.detach().numpy(), gt=b.numpy(), l1=np.float64(l1.item()),
+                        ssim=np.float64(ss.item()), loss=np.float64(total.item()), grad=a.grad.numpy())
+
+
 if __name__ == "__main__":
-    expansion_mesh(); expansion_multi(); sh_colors(); cov3d(); camera(); quat()
+    expansion_mesh(); expansion_multi(); sh_colors(); cov3d(); camera(); quat(); loss()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -120,3 +120,16 @@ def test_projection_matches_reference_geom_transform(golden_dir):
     py = ((g["ndc"][:, 1] + 1.0) * H - 1.0) * 0.5
     np.testing.assert_allclose(st.means2D[vis, 0], px[vis], rtol=1e-5, atol=2e-4)
     np.testing.assert_allclose(st.means2D[vis, 1], py[vis], rtol=1e-5, atol=2e-4)
+
+
+def test_loss_restatement_matches_reference_loss_utils(golden_dir):
+    """gms_b200.losses.training_loss (the fp32 reference of the fused loss kernel) == utils/loss_utils.py."""
+    from gms_b200 import losses
+    g = _load(golden_dir, "loss.npz")
+    a = torch.tensor(g["img"], requires_grad=True); b = torch.tensor(g["gt"])
+    assert abs(losses.l1_loss(a, b).item() - float(g["l1"])) < 1e-7
+    assert abs(losses.ssim(a, b).item() - float(g["ssim"])) < 1e-6
+    total = losses.training_loss(a, b, 0.2)
+    assert abs(total.item() - float(g["loss"])) < 1e-6
+    total.backward()
+    np.testing.assert_allclose(a.grad.numpy(), g["grad"], rtol=1e-4, atol=1e-9)
