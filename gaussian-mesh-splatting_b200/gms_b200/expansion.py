@@ -24,7 +24,8 @@ EPS_S0 = 1e-8   # gaussian_mesh_model.py:43
 
 
 def _f32(t):
-    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.contiguous().float()
+    t = t if (t.dtype == torch.float32 and t.is_contiguous()) else t.contiguous().float()
+    return t.clone() if t.data_ptr() % 16 else t
 
 
 def _stream(device):

@@ -24,9 +24,10 @@ class FlatAdam:
         assert 1 <= len(self.groups) <= 8
         params = [g["param"] for g in self.groups]
         dev = params[0].device
-        n = sum(p.numel() for p in params)
+        pad = lambda k: (k + 63) // 64 * 64     # every segment starts 256-byte aligned (the kernels use 128-bit accesses)
+        n = sum(pad(p.numel()) for p in params)
         self.n = n
-        self.p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -37,7 +38,7 @@ class FlatAdam:
             self.p[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.p[off:off + k].view(p.shape)
             p.grad = self.g[off:off + k].view(p.shape)
-            off += k
+            off += pad(k)
             self.ends.append(off)
         self.betas, self.eps, self.t = betas, eps, 0
 

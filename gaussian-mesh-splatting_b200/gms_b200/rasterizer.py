@@ -39,6 +39,8 @@ class GaussianRasterizationSettings(NamedTuple):
 def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
     if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
         t = t.to(device=device, dtype=torch.float32).contiguous()
+    if t.data_ptr() % 16:      # views at odd offsets: the kernels use 128-bit loads
+        t = t.clone()
     return t
 
 
