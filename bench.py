@@ -53,47 +53,50 @@ def build_scene(name, seed=0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md 'clocks line')."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md 'clocks line'), sampled through NVML
+    every 50 ms from a side thread (same counters nvidia-smi prints; no subprocess start-up hiccup inside the timing)."""
 
-    def __init__(self, gpu_index=0):
+    def __init__(self, gpu_index=0, period_s=0.05):
         super().__init__(daemon=True)
-        self.gpu_index, self.rows, self._stop_evt, self.proc = gpu_index, [], threading.Event(), None
+        self.gpu_index, self.period, self.rows, self._stop_evt = gpu_index, period_s, [], threading.Event()
+        self.active = False     # only samples taken while `active` count
+        self.err = None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-                if self._stop_evt.is_set():
-                    break
-        except Exception:
-            pass
+            import pynvml as nv
+            nv.nvmlInit()
+            phys = self.gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.gpu_index])
+                except Exception:
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            R = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            while not self._stop_evt.is_set():
+                if self.active:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    try:
+                        bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.rows.append((sm, mx, [k for k, b in R.items() if bits & b]))
+                time.sleep(self.period)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def stop(self):
         self._stop_evt.set()
-        if self.proc is not None:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        busy = [x for x in sm if x > 0.5 * max(sm)] or sm
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable: " + str(self.err)]}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({x for r in self.rows for x in r[2]})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
 
 
 def measured_peak_gbs():
@@ -185,6 +188,7 @@ def main():
     ap.add_argument("--workload", default="gs_mesh_1M_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-optimizer", action="store_true", help="exclude the Adam step from the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning knob key=value (gms_set_option), repeatable")
     ap.add_argument("--reference-ops", action="store_true",
                     help="glue ops as the reference orders them (two-step expansion, ATen loss, torch Adam) around our rasterizer")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
@@ -206,6 +210,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K_, W_ = args.steps, max(args.warmup, 3)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        assert _lib.set_option(k, int(v)) >= 0, f"unknown option {k}"
 
     params, cams, dims = build_scene(args.workload)
     F, K, W, H = dims
@@ -249,33 +256,62 @@ def main():
         trainer.step(cams_dev[ci], gts[ci])
         n_frames.append(rasterizer.last_num_rendered)
 
-    cam_buf = torch.empty(35, device=dev)
-    gt_buf = torch.empty(3, H, W, device=dev)
+    # e2e: every step's inputs (ground-truth image 3xHxW fp32 + 35 camera floats) come from PINNED HOST memory; the
+    # copy of step s+1 runs on a side stream while step s computes (a data-loader prefetch), and the step's loss is
+    # read back to the host.  Both copies are inside the timed region.
     from gms_b200.scenes import Camera
+    copy_stream = torch.cuda.Stream(dev)
+    cam_bufs = [torch.empty(35, device=dev) for _ in range(2)]
+    gt_bufs = [torch.empty(3, H, W, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
     h2d = gts_host[0].numel() * 4 + 35 * 4
+
+    def prefetch(s):
+        ci = shard_cameras(len(cams), s, rank, world)
+        b = s & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            gt_bufs[b].copy_(gts_host[ci], non_blocking=True)
+            cam_bufs[b].copy_(cam_host[ci], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    for b in range(2):
+        consumed[b].record(torch.cuda.current_stream(dev))
 
     def step_e2e(s):
         ci = shard_cameras(len(cams), s, rank, world)
-        gt_buf.copy_(gts_host[ci], non_blocking=True)
-        cam_buf.copy_(cam_host[ci], non_blocking=True)
+        b = s & 1
+        prefetch(s + 1)
+        torch.cuda.current_stream(dev).wait_event(ready[b])
         c = cams[ci]
-        cam = Camera(c.image_width, c.image_height, c.FoVx, c.FoVy, cam_buf[:16].view(4, 4), cam_buf[16:32].view(4, 4), cam_buf[32:35])
-        loss = trainer.step(cam, gt_buf)
+        cb = cam_bufs[b]
+        cam = Camera(c.image_width, c.image_height, c.FoVx, c.FoVy, cb[:16].view(4, 4), cb[16:32].view(4, 4), cb[32:35])
+        loss = trainer.step(cam, gt_bufs[b])
+        consumed[b].record(torch.cuda.current_stream(dev))
         return loss.item()     # device -> host read of the step's result
 
-    for s in range(W_):
-        step_resident(s)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for s in range(W_):
+        step_resident(s)
     _lib.launch_count(reset=True)
     n_frames.clear()
+    if sampler:
+        sampler.active = True
     ms_total = timed(step_resident, K_, W_)
+    if sampler:
+        sampler.active = False
     launches = _lib.launch_count(reset=True)
+    prefetch(0)
     for s in range(2):
         step_e2e(s)
-    ms_e2e = timed(step_e2e, K_, W_ + K_)
     if sampler:
+        sampler.active = True
+    ms_e2e = timed(step_e2e, K_, 2)
+    if sampler:
+        sampler.active = False
         sampler.stop()
     # per-kernel device time (CUDA events on the launching stream, inside the library), separate pass
     _lib.set_option("time_kernels", 1)
@@ -316,7 +352,7 @@ def main():
             "steps": K_, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "P": P, "faces": F, "K": K, "width": W, "height": H, "sh_degree": 3,
-                       "cameras": len(cams), "N_mean": N_mean, "optimizer_step": not args.no_optimizer, "glue": "reference-ops" if args.reference_ops else "fused",
+                       "cameras": len(cams), "N_mean": N_mean, "optimizer_step": not args.no_optimizer, "glue": "reference-ops" if args.reference_ops else "fused", "options": args.opt,
                        "parallelism": f"frame-sharded dp{world}", "l2": "inputs_exceed_l2 (per-step working set > 126 MB)",
                        "frame_algo_bytes": frame_bytes, "frame_hbm_frac": frame_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

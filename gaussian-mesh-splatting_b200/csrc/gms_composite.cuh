@@ -48,16 +48,39 @@ __device__ __forceinline__ GmsTileGeom gms_tile_geom(int tile, int gx, int W, in
     return g;
 }
 
-// which of the tile's four 8x8 quads can a splat reach?  (x,y) centre, (ex,ey) conservative half extents
-__device__ __forceinline__ uint32_t gms_quad_mask(float x, float y, float ex, float ey, int tx0, int ty0) {
-    const float xlo = x - ex, xhi = x + ex, ylo = y - ey, yhi = y + ey;
+// Can this splat reach alpha >= 1/255 anywhere in the pixel rectangle [rx0, rx0+7] x [ry0, ry0+7]?
+// i.e. min over the rectangle of 0.5*(cx dx^2 + cz dy^2) + cy dx dy  <=  tau   (tau carries the safety margin).
+__device__ __forceinline__ bool gms_reaches_quad(float x, float y, float cx, float cy, float cz, float tau, float rx0, float ry0) {
+    if (!(tau > 0.f)) return false;                 // opacity < 1/255: never blends
+    if (!(cx > 0.f) || !(cz > 0.f)) return true;    // degenerate conic: be conservative
+    const float rx1 = rx0 + 7.0f, ry1 = ry0 + 7.0f;
+    if (x >= rx0 && x <= rx1 && y >= ry0 && y <= ry1) return true;
+    float best = 3.0e38f;
+    const float icx = __fdividef(1.f, cx), icz = __fdividef(1.f, cz);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        {   // horizontal edge
+            const float dy = y - (e ? ry1 : ry0);
+            const float t = fminf(fmaxf(x + cy * dy * icx, rx0), rx1);
+            const float dx = x - t;
+            best = fminf(best, 0.5f * (cx * dx * dx + cz * dy * dy) + cy * dx * dy);
+        }
+        {   // vertical edge
+            const float dx = x - (e ? rx1 : rx0);
+            const float t = fminf(fmaxf(y + cy * dx * icz, ry0), ry1);
+            const float dy = y - t;
+            best = fminf(best, 0.5f * (cx * dx * dx + cz * dy * dy) + cy * dx * dy);
+        }
+    }
+    return best <= tau;
+}
+
+// which of the tile's four 8x8 quads can a splat reach?
+__device__ __forceinline__ uint32_t gms_quad_mask(float x, float y, float cx, float cy, float cz, float tau, int tx0, int ty0) {
     uint32_t m = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const float qx0 = (float)(tx0 + (q & 1) * 8), qy0 = (float)(ty0 + (q >> 1) * 8);
-        const bool ov = (xhi >= qx0) && (xlo <= qx0 + 7.0f) && (yhi >= qy0) && (ylo <= qy0 + 7.0f);
-        m |= (ov ? 1u : 0u) << q;
-    }
+    for (int q = 0; q < 4; q++)
+        m |= (gms_reaches_quad(x, y, cx, cy, cz, tau, (float)(tx0 + (q & 1) * 8), (float)(ty0 + (q >> 1) * 8)) ? 1u : 0u) << q;
     return m;
 }
 
@@ -99,7 +122,7 @@ k_composite_fwd(const int2* __restrict__ ranges, const uint32_t* __restrict__ po
             s_a[buf][tid] = ra;
             s_b[buf][tid] = rb;
             s_c[buf][tid] = make_float2(rc.x, rc.y);
-            qmask = use_masks ? gms_quad_mask(ra.x, ra.y, rc.z, rc.w, g.tx0, g.ty0) : 0xFu;
+            qmask = use_masks ? gms_quad_mask(ra.x, ra.y, ra.z, ra.w, rb.x, rc.z, g.tx0, g.ty0) : 0xFu;
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -332,7 +355,7 @@ k_composite_bwd(const int2* __restrict__ ranges, const uint32_t* __restrict__ po
         s_id[tid] = id_cur;
         if (id_cur >= 0) {
             s_a[tid] = ra; s_b[tid] = rb; s_c[tid] = make_float2(rc.x, rc.y);
-            qmask = use_masks ? gms_quad_mask(ra.x, ra.y, rc.z, rc.w, g.tx0, g.ty0) : 0xFu;
+            qmask = use_masks ? gms_quad_mask(ra.x, ra.y, ra.z, ra.w, rb.x, rc.z, g.tx0, g.ty0) : 0xFu;
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {

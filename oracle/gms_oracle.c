@@ -64,6 +64,12 @@ static const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570
                                0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                -0.5900435899266435f};
 
+/* Work statistics of the last composite forward (for DESIGN.md / kernel design, not used by any test):
+ * [0] (pixel,splat) pairs visited before the pixel terminated, [1] pairs that blended (alpha >= 1/255),
+ * [2] (8x8 quad, splat) pairs with at least one blending pixel, [3] (tile, splat) pairs with >= 1 blending pixel. */
+static long long g_stats[4];
+void gmso_get_stats(long long* out) { for (int i = 0; i < 4; i++) out[i] = g_stats[i]; }
+
 /* Bounded-sample support for the CPU baseline (bench.py): composite only tiles with tile % stride == 0. */
 static int g_tile_stride = 1;
 void gmso_set_tile_stride(int s) { g_tile_stride = s > 0 ? s : 1; }
@@ -454,18 +460,21 @@ int gmso_composite_forward(const gmso_settings* s, const int32_t* ranges, const 
                            uint8_t* ambiguous /*[H,W] or NULL*/) {
     const int W = s->W, H = s->H;
     const int gx = (W + GMSO_BLOCK - 1) / GMSO_BLOCK, gy = (H + GMSO_BLOCK - 1) / GMSO_BLOCK;
-#pragma omp parallel for schedule(dynamic, 1)
+    long long st0 = 0, st1 = 0, st2 = 0, st3 = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : st0, st1, st2, st3)
     for (int tile = 0; tile < gx * gy; tile++) {
         if (tile % g_tile_stride) continue;
         int tx0 = (tile % gx) * GMSO_BLOCK, ty0 = (tile / gx) * GMSO_BLOCK;
         int r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
+        uint8_t* qhit = (uint8_t*)calloc((size_t)(r1 - r0) + 1, 1);
         for (int py = ty0; py < ty0 + GMSO_BLOCK && py < H; py++)
             for (int px = tx0; px < tx0 + GMSO_BLOCK && px < W; px++) {
+                const int quad = ((py - ty0) >> 3) * 2 + ((px - tx0) >> 3);
                 float T = 1.0f, C[3] = {0.f, 0.f, 0.f}, Dacc = 0.f;
                 int contributor = 0, last = 0; uint8_t amb = 0;
                 float pfx = (float)px, pfy = (float)py;
                 for (int j = r0; j < r1; j++) {
-                    contributor++;
+                    contributor++; st0++;
                     uint32_t g = point_list[j];
                     float dx = means2D[2 * g] - pfx, dy = means2D[2 * g + 1] - pfy;
                     const float* co = conic_opacity + 4 * g;
@@ -482,6 +491,7 @@ int gmso_composite_forward(const gmso_settings* s, const int32_t* ranges, const 
                     Dacc += (1.f / depths[g]) * w;
                     T = test_T;
                     last = contributor;
+                    st1++; qhit[j - r0] |= (uint8_t)(1u << quad);
                 }
                 size_t pix = (size_t)py * W + px;
                 final_T[pix] = T; n_contrib[pix] = last;
@@ -489,7 +499,13 @@ int gmso_composite_forward(const gmso_settings* s, const int32_t* ranges, const 
                 if (out_invdepth) out_invdepth[pix] = Dacc;
                 if (ambiguous) ambiguous[pix] = amb;
             }
+        for (int j = 0; j < r1 - r0; j++) {
+            if (qhit[j]) st3++;
+            st2 += ((qhit[j] >> 0) & 1) + ((qhit[j] >> 1) & 1) + ((qhit[j] >> 2) & 1) + ((qhit[j] >> 3) & 1);
+        }
+        free(qhit);
     }
+    g_stats[0] = st0; g_stats[1] = st1; g_stats[2] = st2; g_stats[3] = st3;
     return 0;
 }
 

@@ -120,6 +120,21 @@ def test_quad_masks_do_not_change_results():
         assert np.abs(a[4][k] - b[4][k]).max() / sc < 1e-4, k   # float atomics: summation order differs
 
 
+@pytest.mark.parametrize("version,tile_order", [(1, 0), (2, 0), (2, 1)])
+def test_composite_generations_agree_and_match_oracle(version, tile_order):
+    """Generation 1 (block-synchronous) and 2 (warp-independent, longest-first tile order) are the same function."""
+    S, g = _case(12000, 352, 272, seed=21, extent=1.0, scale_mu=-2.2)
+    dC, dI = _grads_in(272, 352, 9)
+    old_v, old_o = _lib.set_option("composite_version", version), _lib.set_option("tile_order", tile_order)
+    try:
+        color, radii, invd, state, grads = run_gpu(S, g, dC, dI)
+    finally:
+        _lib.set_option("composite_version", old_v); _lib.set_option("tile_order", old_o)
+    st, gref = run_oracle(S, g, dC, dI)
+    assert_forward_parity(st, color, radii, invd, state)
+    assert_grad_parity(grads, gref)
+
+
 def test_empty_and_invisible_inputs():
     S, g = _case(10, 64, 64, seed=1)
     e = {k: v[:0] for k, v in g.items()}
