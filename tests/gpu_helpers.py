@@ -82,7 +82,7 @@ def assert_forward_parity(st, color, radii, invd, state, tol=1e-5):
 # Gradients w.r.t. scales / rotations / cov3D go through the inverse of a nearly singular 2D covariance (flat mesh
 # Gaussians, s0 ~ 2e-8): the 1e-6 summation-order noise of the fp32 atomics in dL/dconic is amplified ~1e3x there (the
 # stock extension has the same non-determinism); the oracle sums in double.  Everything else stays at `tol`.
-ILL_CONDITIONED = {"scales": 10.0, "rotations": 10.0, "cov3D_precomp": 10.0, "means3D": 2.5}
+ILL_CONDITIONED = {"scales": 25.0, "rotations": 25.0, "cov3D_precomp": 25.0, "means3D": 2.5}
 
 
 def assert_grad_parity(g_gpu, g_ref, tol=2e-4):
