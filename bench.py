@@ -31,6 +31,7 @@ WORKLOADS = {
     "gs_mesh_1M_1080p": (200_000, 5, 1920, 1080, 16),       # BASELINE configs[2] -- the headline
     "gs_mesh_100k_800": (33_334, 3, 800, 800, 8),           # BASELINE configs[1]
     "gs_mesh_500k_1080p": (100_000, 5, 1920, 1080, 16),     # BASELINE configs[4] sizes (training step variant)
+    "gs_multi_mesh_2M_1080p": (400_000, 5, 1920, 1080, 16), # BASELINE configs[3]: 4 meshes x 100k faces x K=5 (merged launch)
     "tiny": (2_000, 3, 320, 240, 4),                        # CI-sized
 }
 ALGO_BYTES = {  # algorithmic bytes per unit, SURVEY.md section 8(d) / DESIGN.md "Roofline accounting"
@@ -45,7 +46,15 @@ ALGO_BYTES = {  # algorithmic bytes per unit, SURVEY.md section 8(d) / DESIGN.md
 def build_scene(name, seed=0):
     from gms_b200 import scenes
     F, K, W, H, ncam = WORKLOADS[name]
-    verts, faces = scenes.object_mesh(F)
+    if name.startswith("gs_multi_mesh"):
+        # 4 disjoint objects, concatenated exactly as gaussian_multi_mesh_model.py:99-119 does (same K => merged once)
+        vs, fs, off = [], [], 0
+        for k, c in enumerate([(-0.75, -0.75, 0.0), (0.75, -0.75, 0.0), (-0.75, 0.75, 0.0), (0.75, 0.75, 0.0)]):
+            v, f = scenes.object_mesh(F // 4)
+            vs.append(v * 0.55 + np.float32(c)); fs.append(f + off); off += v.shape[0]
+        verts, faces = np.concatenate(vs), np.concatenate(fs)
+    else:
+        verts, faces = scenes.object_mesh(F)
     params = scenes.init_mesh_gaussians(verts, faces, K, seed=seed, trained_like=True)
     cams = scenes.ring_cameras(ncam // 2, 3.4, W, H, elevation_deg=15.0) + \
         scenes.ring_cameras(ncam - ncam // 2, 4.4, W, H, elevation_deg=38.0, phase=0.3)
@@ -178,6 +187,61 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- animated render
+def run_render_animated(args, params, cams, dims, dev, world, rank, local):
+    """scripts/render_time_animated.py:68-87 without the PNG writes: per frame t, new_vertices = transform_hotdog_fly(v, t),
+    re-expansion from the moved vertices (gaussian_animated_renderer:61-73) and a rasterizer forward, under no_grad.
+    n_frames = 800, t = linspace(0, 10*pi) (:74), contiguous frame ranges per rank, no collective."""
+    import torch.distributed as dist
+    from gms_b200 import _lib, rasterizer, scenes
+    from gms_b200.model import MeshGaussianModel
+    from gms_b200.trainer import render_frame
+    F, K, W, H = dims
+    model = MeshGaussianModel.from_params(params, dev, packed_features=True)
+    bg = torch.ones(3, device=dev)
+    cams_dev = [c.to(dev) for c in cams]
+    n_frames = 800
+    ts = torch.linspace(0, 10 * math.pi, n_frames)
+    per = n_frames // world
+    lo = rank * per
+    v0 = model.vertices.detach().clone()
+
+    def frame(i):
+        with torch.no_grad():
+            model.vertices.data.copy_(scenes.transform_hotdog_fly(v0, float(ts[lo + (i % per)])))
+            return render_frame(model, cams_dev[i % len(cams_dev)], bg)[0]
+
+    K_, W_ = min(args.steps, per), max(args.warmup, 3)
+    for i in range(W_):
+        frame(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    _lib.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K_):
+        frame(W_ + i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = _lib.launch_count(reset=True)
+    if rank == 0:
+        ms_step = float(ms.item()) / K_
+        print(json.dumps({"metric": "frames/sec (forward only, animated-vertex sweep) @1080p", "value": world * 1000.0 / ms_step,
+                          "unit": "frames/s", "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": ms_step,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": args.workload, "mode": "render_animated", "P": F * K, "faces": F, "K": K, "width": W,
+                                     "height": H, "sh_degree": 3, "n_frames": n_frames, "N_last": rasterizer.last_num_rendered},
+                          "gpu_launches": int(launches)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -188,6 +252,9 @@ def main():
     ap.add_argument("--workload", default="gs_mesh_1M_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-optimizer", action="store_true", help="exclude the Adam step from the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "render_animated"],
+                    help="train: fwd+bwd step (headline). render_animated: scripts/render_time_animated.py path, forward only, "
+                         "vertex animation + re-expansion every frame (BASELINE configs[4])")
     ap.add_argument("--opt", action="append", default=[], help="library tuning knob key=value (gms_set_option), repeatable")
     ap.add_argument("--reference-ops", action="store_true",
                     help="glue ops as the reference orders them (two-step expansion, ATen loss, torch Adam) around our rasterizer")
@@ -217,6 +284,8 @@ def main():
     params, cams, dims = build_scene(args.workload)
     F, K, W, H = dims
     P = F * K
+    if args.mode == "render_animated":
+        return run_render_animated(args, params, cams, dims, dev, world, rank, local)
     model = MeshGaussianModel.from_params(params, dev, packed_features=not args.reference_ops)
     bg = torch.ones(3, device=dev)
     cams_dev = [c.to(dev) for c in cams]

@@ -1,0 +1,321 @@
+// gms_composite3.cuh -- composite forward/backward, generation 3: generation 2 (warp-independent streaming) with the
+// two pixels of a lane computed as ONE packed fp32x2 vector (Blackwell FFMA2 / FMUL2 / FADD2).
+//
+// Why: generation 2 is bound by instruction issue (ncu: 89 % issue-active, IPC 3.37, FMA pipe only 48 % busy;
+// profiles/r1d_composite2_ncu_summary.csv).  A packed instruction retires both pixels' operation in one issue slot.
+// The operations are the same IEEE round-to-nearest mul/add/fma in the same canonical order, so results are
+// bit-identical to generation 2 (tests/test_gpu_parity.py::test_composite_generations_agree_and_match_oracle).
+//
+// Shared-memory slab: every per-splat scalar is stored as a (v, v) pair so that broadcast operands need no packing
+// moves: q0=(x,x,y,y) q1=(conx,conx,-cony,-cony) q2=(conz,conz,op,op) q3=(r,r,g,g) q4=(b,b,1/depth,1/depth).
+//
+// Backward restructuring that removes per-pixel state and branches:
+//  * the stock recurrence keeps (last_alpha, last_color, accum_rec); here the "colour behind" B is advanced at the END
+//    of a splat's step,  B <- alpha*c + (1-alpha)*B , which is the same expression on the same operands, evaluated one
+//    step earlier (bit-identical), and needs no last_* registers;
+//  * a pixel that does not blend a splat (beyond n_contrib, power > 0, alpha < 1/255) uses alpha_eff = 0: then
+//    T/(1-0) = T, B <- 0*c + 1*B = B exactly, and its moment contributions are masked to 0 -- no divergent branch.
+#pragma once
+#include "gms_composite2.cuh"
+
+typedef float2 f2;
+
+__device__ __forceinline__ f2 f2fma(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ f2 f2mul(f2 a, f2 b) {
+    f2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ f2 f2add(f2 a, f2 b) {
+    f2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float gms_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float gms_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct GmsSlab3 {              // pair-duplicated per-splat data
+    float4 q0[GMS_WB];         // x, x, y, y
+    float4 q1[GMS_WB];         // conx, conx, -cony, -cony
+    float4 q2[GMS_WB];         // conz, conz, op, op
+    float4 q3[GMS_WB];         // r, r, g, g
+    float4 q4[GMS_WB];         // b, b, invd, invd
+};
+
+__device__ __forceinline__ void gms_slab3_store(GmsSlab3& S, int lane, const float4& ra, const float4& rb, const float4& rc) {
+    S.q0[lane] = make_float4(ra.x, ra.x, ra.y, ra.y);
+    S.q1[lane] = make_float4(ra.z, ra.z, -ra.w, -ra.w);
+    S.q2[lane] = make_float4(rb.x, rb.x, rb.y, rb.y);
+    S.q3[lane] = make_float4(rb.z, rb.z, rb.w, rb.w);
+    S.q4[lane] = make_float4(rc.x, rc.x, rc.y, rc.y);
+}
+
+// canonical quadratic form for the pixel pair: power = fma(-(cy*dx), dy, -0.5 * fma(cz*dy, dy, (cx*dx)*dx))
+__device__ __forceinline__ f2 gms_power2(const float4& Q0, const float4& Q1, const float4& Q2, f2 npx, f2 npy, f2& dx, f2& dy) {
+    dx = f2add(make_float2(Q0.x, Q0.y), npx);
+    dy = f2add(make_float2(Q0.z, Q0.w), npy);
+    const f2 m1 = f2mul(make_float2(Q1.x, Q1.y), dx);
+    const f2 m2 = f2mul(m1, dx);
+    const f2 nm4 = f2mul(make_float2(Q1.z, Q1.w), dx);          // -(cony*dx): the sign flip is exact
+    const f2 m3 = f2mul(make_float2(Q2.x, Q2.y), dy);
+    const f2 t = f2fma(m3, dy, m2);
+    const f2 h = f2mul(t, make_float2(-0.5f, -0.5f));
+    return f2fma(nm4, dy, h);
+}
+
+// ------------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(GMS_CB)
+k_composite_fwd3(const int2* __restrict__ ranges, const int* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
+                 const float4* __restrict__ recs, int W, int H, int gx, const float* __restrict__ bg,
+                 float* __restrict__ out_color, float* __restrict__ final_T, int* __restrict__ n_contrib,
+                 float* __restrict__ out_invdepth) {
+    __shared__ GmsSlab3 s_slab[4][2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;
+    const GmsTileGeom g = gms_tile_geom(tile, gx, W, H, warp, lane);
+    const int2 rng = ranges[tile];
+    const int n = rng.y - rng.x;
+    const f2 npx = make_float2(-(float)g.px, -(float)g.px);
+    const f2 npy = make_float2(-(float)g.py0, -(float)(g.py0 + 1));
+    const float qx0 = (float)(g.tx0 + (warp & 1) * 8), qy0 = (float)(g.ty0 + (warp >> 1) * 8);
+
+    f2 T = make_float2(1.f, 1.f), D = make_float2(0.f, 0.f);
+    f2 Cr = D, Cg = D, Cb = D;
+    int last0 = 0, last1 = 0;
+    bool live0 = g.in0, live1 = g.in1;
+
+    int id_cur = (lane < n) ? (int)point_list[rng.x + lane] : -1;
+    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
+    if (id_cur >= 0) { ra = recs[3 * id_cur]; rb = recs[3 * id_cur + 1]; rc = recs[3 * id_cur + 2]; }
+    int id_nx = (GMS_WB + lane < n) ? (int)point_list[rng.x + GMS_WB + lane] : -1;
+
+    for (int base = 0; base < n; base += GMS_WB) {
+        if (!__any_sync(0xffffffffu, live0 || live1)) break;
+        GmsSlab3& S = s_slab[warp][(base >> 5) & 1];
+        bool hit = false;
+        if (id_cur >= 0) {
+            hit = gms_reaches_quad(ra.x, ra.y, ra.z, ra.w, rb.x, rc.z, qx0, qy0);
+            if (hit) gms_slab3_store(S, lane, ra, rb, rc);
+        }
+        uint32_t m = __ballot_sync(0xffffffffu, hit);
+        id_cur = id_nx;
+        if (id_cur >= 0) { ra = recs[3 * id_cur]; rb = recs[3 * id_cur + 1]; rc = recs[3 * id_cur + 2]; }
+        {
+            const int k = base + 2 * GMS_WB + lane;
+            id_nx = (k < n) ? (int)point_list[rng.x + k] : -1;
+        }
+        __syncwarp();
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const float4 Q0 = S.q0[j], Q1 = S.q1[j], Q2 = S.q2[j];
+            const int pos = base + j + 1;
+            f2 dx, dy;
+            const f2 power = gms_power2(Q0, Q1, Q2, npx, npy, dx, dy);
+            const f2 sc = f2mul(power, make_float2(GMS_LOG2E, GMS_LOG2E));
+            const f2 G = make_float2(gms_ex2(sc.x), gms_ex2(sc.y));
+            const f2 araw = f2mul(make_float2(Q2.z, Q2.w), G);
+            const f2 alpha = make_float2(fminf(GMS_ALPHA_MAX, araw.x), fminf(GMS_ALPHA_MAX, araw.y));
+            const f2 oma = f2fma(alpha, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));     // 1 - alpha, one rounding
+            const f2 testT = f2mul(T, oma);
+            bool ok0 = live0 && power.x <= 0.0f && alpha.x >= GMS_ALPHA_MIN;
+            bool ok1 = live1 && power.y <= 0.0f && alpha.y >= GMS_ALPHA_MIN;
+            if (ok0 && testT.x < GMS_T_STOP) { live0 = false; ok0 = false; }
+            if (ok1 && testT.y < GMS_T_STOP) { live1 = false; ok1 = false; }
+            if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+            const float4 Q3 = S.q3[j], Q4 = S.q4[j];
+            f2 w = f2mul(alpha, T);
+            w.x = ok0 ? w.x : 0.f; w.y = ok1 ? w.y : 0.f;
+            Cr = f2fma(make_float2(Q3.x, Q3.y), w, Cr);
+            Cg = f2fma(make_float2(Q3.z, Q3.w), w, Cg);
+            Cb = f2fma(make_float2(Q4.x, Q4.y), w, Cb);
+            D = f2fma(make_float2(Q4.z, Q4.w), w, D);
+            T.x = ok0 ? testT.x : T.x; T.y = ok1 ? testT.y : T.y;
+            last0 = ok0 ? pos : last0; last1 = ok1 ? pos : last1;
+        }
+        __syncwarp();
+    }
+    const size_t HW = (size_t)H * W;
+    const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+    if (g.in0) {
+        const size_t pix = (size_t)g.py0 * W + g.px;
+        final_T[pix] = T.x; n_contrib[pix] = last0;
+        out_color[pix] = fmaf(T.x, bg0, Cr.x); out_color[HW + pix] = fmaf(T.x, bg1, Cg.x);
+        out_color[2 * HW + pix] = fmaf(T.x, bg2, Cb.x);
+        out_invdepth[pix] = D.x;
+    }
+    if (g.in1) {
+        const size_t pix = (size_t)(g.py0 + 1) * W + g.px;
+        final_T[pix] = T.y; n_contrib[pix] = last1;
+        out_color[pix] = fmaf(T.y, bg0, Cr.y); out_color[HW + pix] = fmaf(T.y, bg1, Cg.y);
+        out_color[2 * HW + pix] = fmaf(T.y, bg2, Cb.y);
+        out_invdepth[pix] = D.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+struct GmsSlab3B {
+    float4 q0[GMS_WB], q1[GMS_WB], q2[GMS_WB], q3[GMS_WB], q4[GMS_WB];
+    int id[GMS_WB];
+    float part[GMS_WB][12];
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(GMS_CB, MINB)
+k_composite_bwd3(const int2* __restrict__ ranges, const int* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
+                 const float4* __restrict__ recs, int W, int H, int gx, const float* __restrict__ bg,
+                 const float* __restrict__ final_T, const int* __restrict__ n_contrib,
+                 const float* __restrict__ dL_dpix, const float* __restrict__ dL_dinv, float4* __restrict__ dgeom) {
+    __shared__ GmsSlab3B s_slab[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;
+    const GmsTileGeom g = gms_tile_geom(tile, gx, W, H, warp, lane);
+    const int2 rng = ranges[tile];
+    const f2 npx = make_float2(-(float)g.px, -(float)g.px);
+    const f2 npy = make_float2(-(float)g.py0, -(float)(g.py0 + 1));
+    const float qx0 = (float)(g.tx0 + (warp & 1) * 8), qy0 = (float)(g.ty0 + (warp >> 1) * 8);
+    const size_t HW = (size_t)H * W;
+    const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
+    GmsSlab3B& S = s_slab[warp];
+
+    // per-pixel-pair state
+    f2 T, nTfin, dpr, dpg, dpb, dpd, bgdot;
+    int lastA = 0, lastB = 0;
+    {
+        float tf[2] = {1.f, 1.f}, r[2] = {0.f, 0.f}, gg[2] = {0.f, 0.f}, b[2] = {0.f, 0.f}, dd[2] = {0.f, 0.f};
+        int la[2] = {0, 0};
+        const bool in[2] = {g.in0, g.in1};
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (in[k]) {
+                const size_t pix = (size_t)(g.py0 + k) * W + g.px;
+                tf[k] = final_T[pix]; la[k] = n_contrib[pix];
+                r[k] = dL_dpix[pix]; gg[k] = dL_dpix[HW + pix]; b[k] = dL_dpix[2 * HW + pix];
+                dd[k] = dL_dinv ? dL_dinv[pix] : 0.f;
+            }
+        }
+        const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+        T = make_float2(tf[0], tf[1]); nTfin = make_float2(-tf[0], -tf[1]);
+        dpr = make_float2(r[0], r[1]); dpg = make_float2(gg[0], gg[1]); dpb = make_float2(b[0], b[1]); dpd = make_float2(dd[0], dd[1]);
+        bgdot = make_float2(bg0 * r[0] + bg1 * gg[0] + bg2 * b[0], bg0 * r[1] + bg1 * gg[1] + bg2 * b[1]);
+        lastA = la[0]; lastB = la[1];
+    }
+    f2 Br = make_float2(0.f, 0.f), Bg = Br, Bb = Br, Bd = Br;     // colour / inverse depth accumulated behind
+    const int wlast = __reduce_max_sync(0xffffffffu, max(lastA, lastB));
+    if (wlast <= 0) return;
+    const int nb = (wlast + GMS_WB - 1) / GMS_WB;
+
+    int id_cur;
+    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
+    {
+        const int k = (nb - 1) * GMS_WB + lane;
+        id_cur = (k < wlast) ? (int)point_list[rng.x + k] : -1;
+        if (id_cur >= 0) { ra = recs[3 * id_cur]; rb = recs[3 * id_cur + 1]; rc = recs[3 * id_cur + 2]; }
+    }
+    int id_nx = (nb >= 2) ? (int)point_list[rng.x + (nb - 2) * GMS_WB + lane] : -1;
+
+    for (int b = nb - 1; b >= 0; b--) {
+        bool hit = false;
+        S.id[lane] = id_cur;
+        if (id_cur >= 0) {
+            hit = gms_reaches_quad(ra.x, ra.y, ra.z, ra.w, rb.x, rc.z, qx0, qy0);
+            if (hit) gms_slab3_store(reinterpret_cast<GmsSlab3&>(S), lane, ra, rb, rc);
+        }
+        uint32_t m = __ballot_sync(0xffffffffu, hit);
+        id_cur = id_nx;
+        if (id_cur >= 0) { ra = recs[3 * id_cur]; rb = recs[3 * id_cur + 1]; rc = recs[3 * id_cur + 2]; }
+        id_nx = (b >= 2) ? (int)point_list[rng.x + (b - 2) * GMS_WB + lane] : -1;
+        __syncwarp();
+        uint32_t touched = 0;
+        while (m) {
+            const int j = 31 - __clz(m);
+            m &= ~(1u << j);
+            const int pos = b * GMS_WB + j;
+            const float4 Q0 = S.q0[j], Q1 = S.q1[j], Q2 = S.q2[j];
+            f2 dx, dy;
+            const f2 power = gms_power2(Q0, Q1, Q2, npx, npy, dx, dy);
+            const f2 sc = f2mul(power, make_float2(GMS_LOG2E, GMS_LOG2E));
+            const f2 G = make_float2(gms_ex2(sc.x), gms_ex2(sc.y));
+            const f2 araw = f2mul(make_float2(Q2.z, Q2.w), G);
+            const float a0 = fminf(GMS_ALPHA_MAX, araw.x), a1 = fminf(GMS_ALPHA_MAX, araw.y);
+            const bool v0 = pos < lastA && power.x <= 0.0f && a0 >= GMS_ALPHA_MIN;
+            const bool v1 = pos < lastB && power.y <= 0.0f && a1 >= GMS_ALPHA_MIN;
+            if (!__any_sync(0xffffffffu, v0 || v1)) continue;
+            const float4 Q3 = S.q3[j], Q4 = S.q4[j];
+            const f2 alpha = make_float2(v0 ? a0 : 0.f, v1 ? a1 : 0.f);
+            const f2 oma = f2fma(alpha, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+            const f2 inv = make_float2(gms_rcp(oma.x), gms_rcp(oma.y));
+            T = f2mul(T, inv);
+            const f2 w = f2mul(alpha, T);
+            const f2 cr = make_float2(Q3.x, Q3.y), cg = make_float2(Q3.z, Q3.w), cb = make_float2(Q4.x, Q4.y), cd = make_float2(Q4.z, Q4.w);
+            const f2 neg1 = make_float2(-1.f, -1.f);
+            // dL/dalpha = sum_c (c - B_c) * dL/dC_c   (then * T, + background term)
+            f2 dLa = f2mul(f2fma(Br, neg1, cr), dpr);
+            dLa = f2fma(f2fma(Bg, neg1, cg), dpg, dLa);
+            dLa = f2fma(f2fma(Bb, neg1, cb), dpb, dLa);
+            dLa = f2fma(f2fma(Bd, neg1, cd), dpd, dLa);
+            // advance "behind": B <- alpha*c + (1-alpha)*B
+            Br = f2fma(alpha, cr, f2mul(oma, Br)); Bg = f2fma(alpha, cg, f2mul(oma, Bg));
+            Bb = f2fma(alpha, cb, f2mul(oma, Bb)); Bd = f2fma(alpha, cd, f2mul(oma, Bd));
+            dLa = f2mul(dLa, T);
+            dLa = f2fma(f2mul(nTfin, inv), bgdot, dLa);
+            f2 q = f2mul(dLa, G);
+            q.x = v0 ? q.x : 0.f; q.y = v1 ? q.y : 0.f;
+            const f2 qx = f2mul(q, dx), qy = f2mul(q, dy);
+            const f2 pxx = f2mul(qx, dx), pxy = f2mul(qx, dy), pyy = f2mul(qy, dy);
+            const f2 wr = f2mul(w, dpr), wg = f2mul(w, dpg), wb = f2mul(w, dpb), wd = f2mul(w, dpd);
+            float v[10];
+            v[0] = qx.x + qx.y; v[1] = qy.x + qy.y; v[2] = pxx.x + pxx.y; v[3] = pxy.x + pxy.y; v[4] = pyy.x + pyy.y;
+            v[5] = q.x + q.y; v[6] = wr.x + wr.y; v[7] = wg.x + wg.y; v[8] = wb.x + wb.y; v[9] = wd.x + wd.y;
+            float out; int idx; bool valid;
+            gms_fold10(v, lane, out, idx, valid);
+            if (valid) S.part[j][idx] = out;
+            touched |= 1u << j;
+        }
+        __syncwarp();
+        if ((touched >> lane) & 1u) {
+            const int id = S.id[lane];
+            const float4 s0 = *reinterpret_cast<const float4*>(&S.part[lane][0]);
+            const float4 s1 = *reinterpret_cast<const float4*>(&S.part[lane][4]);
+            const float2 s2 = *reinterpret_cast<const float2*>(&S.part[lane][8]);
+            const float4 Q1 = S.q1[lane], Q2 = S.q2[lane];
+            const float conx = Q1.x, ncony = Q1.z, conz = Q2.x, op = Q2.z;
+            float4 g0, g1;
+            g0.x = (-conx * s0.x + ncony * s0.y) * op * halfW;  // dL/dmean2D.x (NDC-scaled)
+            g0.y = (-conz * s0.y + ncony * s0.x) * op * halfH;  // dL/dmean2D.y
+            g0.z = -0.5f * op * s0.z;                           // dL/dconic.x
+            g0.w = -0.5f * op * s0.w;                           // dL/dconic.y (stock half convention)
+            g1.x = -0.5f * op * s1.x;                           // dL/dconic.z
+            g1.y = s1.y;                                        // dL/d(conic_opacity.w)
+            g1.z = s1.z; g1.w = s1.w;                           // dL/drgb.r, .g
+            atomicAdd(&dgeom[3 * id], g0);
+            atomicAdd(&dgeom[3 * id + 1], g1);
+            atomicAdd(reinterpret_cast<float2*>(&dgeom[3 * id + 2]), s2);   // dL/drgb.b, dL/dinvdepth
+        }
+        __syncwarp();
+    }
+}

@@ -113,3 +113,37 @@ class MeshGaussianModel:
                   {"params": [self._scale], "lr": scaling_lr, "name": "scaling"}]
         self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
         return self.optimizer
+
+
+class MultiMeshGaussianModel(MeshGaussianModel):
+    """gs_multi_mesh: several meshes, one Gaussian set (games/multi_mesh_splatting/scene/gaussian_multi_mesh_model.py).
+
+    The reference keeps per-mesh lists (vertices / faces / _alpha / _scale) and loops `expand -> torch.cat`
+    (:99-119, :121-174, :176-199).  Per-face work is independent of which mesh a face belongs to, so when every mesh
+    uses the same K the meshes are merged ONCE at construction (faces re-indexed into one vertex array) and the whole
+    set runs through the single-mesh kernels: one launch instead of a loop, no concatenation.  Meshes with different K
+    keep the reference's loop (`expand_per_mesh`)."""
+
+    @classmethod
+    def from_mesh_params(cls, plist, device="cuda", sh_degree: int = 3, active_sh_degree: int = 3, packed_features: bool = False):
+        Ks = {p._alpha.shape[1] for p in plist}
+        if len(Ks) != 1:
+            raise ValueError("merged fast path needs one K; use expand_per_mesh for heterogeneous K")
+        off, faces = 0, []
+        for p in plist:
+            faces.append(p.faces + off)
+            off += p.vertices.shape[0]
+        merged = MeshGaussianParams(torch.cat([p.vertices for p in plist]), torch.cat(faces),
+                                    torch.cat([p._alpha for p in plist]), torch.cat([p._scale for p in plist]),
+                                    torch.cat([p._features_dc for p in plist]), torch.cat([p._features_rest for p in plist]),
+                                    torch.cat([p._opacity for p in plist]))
+        m = cls.from_params(merged, device, sh_degree, active_sh_degree, packed_features)
+        m.mesh_face_counts = [p.faces.shape[0] for p in plist]
+        return m
+
+    @staticmethod
+    def expand_per_mesh(vertices_list, faces_list, alpha_list, scale_list, eps: float = expansion.EPS_S0):
+        """Reference-shaped path for heterogeneous K: per-mesh fused launch, then cat (-> xyz, _scaling, _rotation)."""
+        outs = [expansion.expand(v, f, a, s, eps, activated=False)[:3] for v, f, a, s in
+                zip(vertices_list, faces_list, alpha_list, scale_list)]
+        return tuple(torch.cat([o[i] for o in outs]) for i in range(3))

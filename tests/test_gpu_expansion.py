@@ -106,3 +106,46 @@ def test_whole_frame_gradients_reach_mesh_parameters():
         sc_ = b.abs().max().item() + 1e-20
         err = (a.cpu() - b).abs().max().item() / sc_
         assert err < 2e-3, f"{name}: {err:.3e}"
+
+
+def test_multi_mesh_matches_reference_golden_and_merged_path(golden_dir):
+    """gs_multi_mesh: per-mesh loop + cat (heterogeneous K) against the reference's GaussianMultiMeshModel output; and the
+    merged single-launch path (equal K) against the per-mesh loop."""
+    from gms_b200.model import MultiMeshGaussianModel
+    g = np.load(os.path.join(golden_dir, "expansion_multi.npz"))
+    n = int(g["n_mesh"])
+    dev = "cuda"
+    vs = [torch.tensor(g[f"vertices{k}"], device=dev) for k in range(n)]
+    fs = [torch.tensor(g[f"faces{k}"], device=dev) for k in range(n)]
+    als = [torch.tensor(g[f"_alpha{k}"], device=dev) for k in range(n)]
+    scs = [torch.tensor(g[f"_scale{k}"], device=dev) for k in range(n)]
+    xyz, sl, rr = MultiMeshGaussianModel.expand_per_mesh(vs, fs, als, scs)
+    np.testing.assert_allclose(xyz.cpu().numpy(), g["xyz"], atol=1e-6)
+    np.testing.assert_allclose(sl.cpu().numpy(), g["_scaling"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(rr.cpu().numpy(), g["_rotation"], atol=1e-6)
+    # merged fast path (same K): identical to the loop
+    plist = [scenes.init_mesh_gaussians(*scenes.icosphere(2, radius=0.4 + 0.2 * k), K=3, seed=k) for k in range(3)]
+    for k, p in enumerate(plist):
+        p.vertices += torch.tensor([1.2 * k, 0.0, 0.0])
+    m = MultiMeshGaussianModel.from_mesh_params(plist, dev)
+    x1, s1, r1 = m.expand_fused(activated=False)
+    x2, s2, r2 = MultiMeshGaussianModel.expand_per_mesh([p.vertices.to(dev) for p in plist], [p.faces.to(dev) for p in plist],
+                                                        [p._alpha.to(dev) for p in plist], [p._scale.to(dev) for p in plist])
+    assert torch.equal(x1, x2) and torch.equal(s1, s2) and torch.equal(r1, r2)
+
+
+def test_animated_path_reexpands_from_triangles():
+    """renderer/gaussian_animated_renderer/__init__.py:61-73: xyz = alpha @ triangles and prepare_scaling_rot() from the
+    TRANSFORMED triangles; our two-step ops follow the moved vertices exactly like the oracle."""
+    p = scenes.init_mesh_gaussians(*scenes.icosphere(3), K=4, seed=9)
+    dev = "cuda"
+    m = MeshGaussianModel.from_params(p, dev)
+    v_new = scenes.transform_hotdog_fly(p.vertices, 7.5)
+    tri = v_new[p.faces].to(dev)
+    m.triangles = tri
+    m.prepare_scaling_rot()
+    xyz = torch.matmul(m.alpha, tri).reshape(-1, 3)
+    oxyz, osl, orr, _, _ = oexp.expand(v_new, p.faces, p._alpha, p._scale)
+    np.testing.assert_allclose(xyz.detach().cpu().numpy(), oxyz.numpy(), atol=2e-6)
+    np.testing.assert_allclose(m._scaling.detach().cpu().numpy(), osl.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(m._rotation.detach().cpu().numpy(), orr.numpy(), atol=2e-6)
