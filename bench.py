@@ -212,7 +212,7 @@ def run_render_animated(args, params, cams, dims, dev, world, rank, local):
             return render_frame(model, cams_dev[i % len(cams_dev)], bg)[0]
 
     K_, W_ = min(args.steps, per), max(args.warmup, 3)
-    for i in range(W_):
+    for i in range(max(W_, 2 * len(cams_dev))):
         frame(i)
     if world > 1:
         dist.barrier()
@@ -363,7 +363,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    for s in range(W_):
+    for s in range(max(W_, len(cams))):      # warm-up covers one sweep of the cameras (allocator sees every scratch size)
         step_resident(s)
     _lib.launch_count(reset=True)
     n_frames.clear()

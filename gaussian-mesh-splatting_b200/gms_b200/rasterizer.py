@@ -61,20 +61,31 @@ last_num_rendered = 0   # N of the most recent forward (statistics for bench.py)
 
 
 class _Scratch:
-    """Serves the three scratch regions from torch uint8 tensors and keeps them alive for backward."""
+    """Holds the three scratch regions (torch uint8 tensors) alive for backward.  The ctypes callback that fills it is
+    created per call and dropped right after the forward returns: keeping it would tie callback <-> owner into a
+    reference cycle and leave ~300 MB per frame to the cyclic GC (measured: 2.6 -> 8.8 ms/step)."""
 
     def __init__(self, device):
         self.device = device
         self.bufs = {}
-        self.cb = _lib.ALLOC_FN(self._alloc)
 
-    def _alloc(self, user, which, nbytes):
+
+def _make_alloc_callback(bufs: dict, device):
+    def _alloc(user, which, nbytes):
+        # The binning region scales with N, which changes with every camera: round it up to 64 MiB steps so the
+        # caching allocator sees a handful of sizes instead of a new one per frame (a fresh cudaMalloc is a device sync).
+        nbytes = int(nbytes)
+        if which == _lib.BUF_BINNING:
+            step = 64 << 20
+            nbytes = (nbytes + step - 1) // step * step
         try:
-            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            t = torch.empty(nbytes, dtype=torch.uint8, device=device)
         except Exception:
             return 0
-        self.bufs[int(which)] = t
+        bufs[int(which)] = t
         return t.data_ptr()
+
+    return _lib.ALLOC_FN(_alloc)
 
 
 def _settings_struct(rs: GaussianRasterizationSettings, device, keep: list) -> _lib.RasterSettings:
@@ -126,8 +137,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         scratch = _Scratch(device)
         saved = _lib.RasterSaved()
         stream = torch.cuda.current_stream(device).cuda_stream
+        cb = _make_alloc_callback(scratch.bufs, device)
         with torch.cuda.device(device):
-            rc = L.gms_rasterize_forward(C.byref(s), C.byref(i), C.byref(o), scratch.cb, None, C.byref(saved), stream)
+            rc = L.gms_rasterize_forward(C.byref(s), C.byref(i), C.byref(o), cb, None, C.byref(saved), stream)
+        del cb
         if rc != 0 and raster_settings.debug:
             try:
                 torch.save(tuple(t.cpu() if isinstance(t, torch.Tensor) else t for t in
