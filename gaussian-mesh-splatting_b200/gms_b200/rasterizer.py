@@ -58,6 +58,10 @@ def _ptr(t: Optional[torch.Tensor]):
 KEEP_DEBUG = False      # tests set this to True to keep the last forward's scratch reachable
 last_debug = None
 last_num_rendered = 0   # N of the most recent forward (statistics for bench.py)
+# When True and `shs` is a leaf whose .grad is a preallocated, zeroed, contiguous buffer (FlatAdam's contract), the
+# backward kernel writes dL/dshs (192 B/Gaussian, the largest gradient) straight into it and autograd gets None:
+# saves the AccumulateGrad read-modify-write over 3 x 192 MB per frame.  Off by default (plain autograd semantics).
+DIRECT_SH_GRAD = False
 
 
 class _Scratch:
@@ -154,6 +158,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         if KEEP_DEBUG:
             global last_debug
             last_debug = dict(scratch=scratch, num_rendered=int(saved.num_rendered), P=P, W=W, H=H, radii=radii)
+        ctx.sh_sink = None
+        if DIRECT_SH_GRAD and sh is not None and shs is not None and sh.is_leaf and sh.grad is not None and \
+                sh.grad.is_contiguous() and sh.grad.shape == shs.shape and sh.grad.dtype == torch.float32 and \
+                sh.grad.data_ptr() % 16 == 0 and sh.data_ptr() == shs.data_ptr():
+            ctx.sh_sink = sh.grad
         ctx.raster_settings = raster_settings
         ctx.num_rendered = int(saved.num_rendered)
         ctx.scratch = scratch
@@ -182,7 +191,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         gdep = None if grad_out_depth is None else _dev_f32(grad_out_depth, device)
         e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
         g_m3, g_m2, g_op = e(P, 3), e(P, 3), e(P, 1)
-        g_sh = e(P, M, 3) if shs is not None else None
+        sink = ctx.sh_sink
+        g_sh = (sink if sink is not None else e(P, M, 3)) if shs is not None else None
         g_col = e(P, 3) if col is not None else None
         g_sc = e(P, 3) if sc is not None else None
         g_rot = e(P, 4) if rot is not None else None
@@ -202,6 +212,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         if P == 0:
             z = lambda t: None if t is None else torch.zeros_like(t)
             g_m3, g_m2, g_op, g_sh, g_col, g_sc, g_rot, g_cov = map(z, (g_m3, g_m2, g_op, g_sh, g_col, g_sc, g_rot, g_cov))
+        if sink is not None:
+            g_sh = None      # already written in place
         return g_m3, g_m2, g_sh, g_col, g_op, g_sc, g_rot, g_cov, None
 
 

@@ -79,6 +79,8 @@ class MeshTrainer:
                     p.grad.mul_(1.0 / self.world)
 
     def step(self, cam: Camera, gt: torch.Tensor) -> torch.Tensor:
+        from . import rasterizer as _r
+        _r.DIRECT_SH_GRAD = self.fast      # FlatAdam keeps .grad preallocated and zeroed: write dL/dshs in place
         image, radii, _ = render_frame(self.model, cam, self.bg, fused=self.fast)
         loss = fused_training_loss(image, gt, self.lambda_dssim) if self.fast else training_loss(image, gt, self.lambda_dssim)
         loss.backward()
