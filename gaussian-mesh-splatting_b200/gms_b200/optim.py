@@ -18,19 +18,26 @@ REFERENCE_LRS = dict(vertices=0.0, alpha=0.001, f_dc=0.0025, f_rest=0.0025 / 20.
 
 
 class FlatAdam:
-    def __init__(self, groups: Sequence[dict], betas=(0.9, 0.999), eps: float = 1e-15):
-        """groups: dicts with `param` and either `lr`, or (`lr0`, `lr1`, `inner`, `period`) for the packed SH tensor."""
+    def __init__(self, groups: Sequence[dict], betas=(0.9, 0.999), eps: float = 1e-15, world: int = 1, rank: int = 0):
+        """groups: dicts with `param` and either `lr`, or (`lr0`, `lr1`, `inner`, `period`) for the packed SH tensor.
+        world > 1: SHARDED optimizer (ZeRO-1 style).  The gradient exchange is a reduce-scatter, every rank keeps Adam
+        moments for and updates only its 1/world slice of the flat buffer, and an all-gather brings the updated
+        parameters back -- the same bytes on NVLink as an all-reduce, but the 28 B/parameter Adam pass shrinks by `world`."""
         self.groups = list(groups)
+        self.world, self.rank = int(world), int(rank)
         assert 1 <= len(self.groups) <= 8
         params = [g["param"] for g in self.groups]
         dev = params[0].device
         pad = lambda k: (k + 63) // 64 * 64     # every segment starts 256-byte aligned (the kernels use 128-bit accesses)
         n = sum(pad(p.numel()) for p in params)
+        n = (n + 64 * self.world - 1) // (64 * self.world) * (64 * self.world)     # equal, 256-byte aligned shards
         self.n = n
+        self.shard = n // self.world
         self.p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.g = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(self.shard, dtype=torch.float32, device=dev)      # moments: this rank's slice only
+        self.v = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self.g_shard = torch.zeros(self.shard, dtype=torch.float32, device=dev) if self.world > 1 else None
         off = 0
         self.ends = []
         for p in params:
@@ -50,9 +57,22 @@ class FlatAdam:
         self.g.zero_()
 
     def step(self):
+        """world == 1: one launch over the whole flat buffer (gradient zeroed in the same pass).
+        world > 1: reduce-scatter(mean) -> Adam on the local slice -> all-gather of the parameters; the full gradient
+        buffer is re-zeroed with one memset."""
+        import torch.distributed as dist
         self.t += 1
         a = _lib.AdamArgs()
-        a.n, a.p, a.g, a.m, a.v = self.n, self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
+        if self.world > 1:
+            dist.reduce_scatter_tensor(self.g_shard, self.g, op=dist.ReduceOp.SUM)
+            self.g_shard.mul_(1.0 / self.world)
+            off = self.rank * self.shard
+            p_local = self.p[off:off + self.shard]
+            a.n, a.offset = self.shard, off
+            a.p, a.g, a.m, a.v = p_local.data_ptr(), self.g_shard.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
+        else:
+            a.n, a.offset = self.n, 0
+            a.p, a.g, a.m, a.v = self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
         a.nseg = len(self.groups)
         for i, g in enumerate(self.groups):
             a.seg_end[i] = self.ends[i]
@@ -64,6 +84,9 @@ class FlatAdam:
         dev = self.p.device
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gms_adam_step(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "gms_adam_step")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.p, p_local)
+            self.g.zero_()
 
 
 def mesh_model_groups(model, lrs=REFERENCE_LRS) -> List[dict]:

@@ -60,7 +60,7 @@ class MeshTrainer:
         self.optimizer_step = optimizer_step
         self.fast = fast
         if fast:
-            self.opt = FlatAdam(mesh_model_groups(model))
+            self.opt = FlatAdam(mesh_model_groups(model), world=world, rank=rank)   # sharded over the ranks when world > 1
             self.flat_grad = self.opt.flat_grad
         else:
             self.opt = model.training_setup()
@@ -69,6 +69,8 @@ class MeshTrainer:
     def _all_reduce(self):
         if self.world <= 1:
             return
+        if self.fast and self.optimizer_step:
+            return      # FlatAdam.step() does reduce-scatter / sharded update / all-gather itself
         if self.flat_grad is not None:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
             self.flat_grad.mul_(1.0 / self.world)

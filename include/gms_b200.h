@@ -218,8 +218,9 @@ int gms_l1_ssim_loss(const gms_loss_args* a, void* cuda_stream);
  * Segment i covers flat indices [seg_end[i-1], seg_end[i]); lr = lr0[i], or -- when period[i] > 0 --
  * lr0[i] where ((index - segment start) / inner[i]) % period[i] == 0 and lr1[i] elsewhere (DC vs rest SH). */
 typedef struct gms_adam_args {
-    int64_t n;
-    float* p; float* g; float* m; float* v;
+    int64_t n;               /* elements this call updates */
+    int64_t offset;          /* flat index of element 0 (sharded optimizer: each rank updates [offset, offset+n)); 0 otherwise */
+    float* p; float* g; float* m; float* v;   /* pointers to element `offset` of the respective flat buffers */
     int32_t nseg;
     int64_t seg_end[8];
     float lr0[8]; float lr1[8];
