@@ -38,6 +38,8 @@ def main():
     # single-process reference on every rank: average the per-camera gradients by hand
     r = MeshGaussianModel.from_params(p, dev, packed_features=True)
     rt = MeshTrainer(r, bg, world=1, rank=0, fast=True)
+    from gms_b200 import rasterizer
+    rasterizer.DIRECT_SH_GRAD = False      # two frames accumulate into one gradient here: plain autograd accumulation
     for s in range(3):
         for q in range(world):
             ci = shard_cameras(len(cams), s, q, world)

@@ -135,6 +135,21 @@ def test_composite_generations_agree_and_match_oracle(version, tile_order):
     assert_grad_parity(grads, gref)
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("P,W,H", [(50000, 640, 480), (300, 48, 32), (5000, 1920, 1080)])
+def test_sort_implementations_give_the_stock_order(impl, P, W, H):
+    """Hand-written radix sort (1) and cub (0): identical, oracle-exact (tile, depth bits, index) order; sizes chosen to
+    hit partial CTAs, > 1 scan chunk, and 13 tile bits (two passes) / 7 tile bits (one pass)."""
+    S, g = _case(P, W, H, seed=P + impl, extent=1.1, scale_mu=-2.4)
+    old = _lib.set_option("sort_impl", impl)
+    try:
+        color, radii, invd, state, _ = run_gpu(S, g)
+    finally:
+        _lib.set_option("sort_impl", old)
+    st, _ = run_oracle(S, g)
+    assert_forward_parity(st, color, radii, invd, state)
+
+
 def test_empty_and_invisible_inputs():
     S, g = _case(10, 64, 64, seed=1)
     e = {k: v[:0] for k, v in g.items()}
