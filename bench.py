@@ -256,6 +256,7 @@ def main():
                     help="train: fwd+bwd step (headline). render_animated: scripts/render_time_animated.py path, forward only, "
                          "vertex animation + re-expansion every frame (BASELINE configs[4])")
     ap.add_argument("--opt", action="append", default=[], help="library tuning knob key=value (gms_set_option), repeatable")
+    ap.add_argument("--no-native", action="store_true", help="drive the frame through PyTorch autograd instead of the one-call gms_train_frame")
     ap.add_argument("--reference-ops", action="store_true",
                     help="glue ops as the reference orders them (two-step expansion, ATen loss, torch Adam) around our rasterizer")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
@@ -298,7 +299,8 @@ def main():
     gts_host = [g.cpu().pin_memory() for g in gts]
     cam_host = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center.reshape(-1)]).pin_memory()
                 for c in cams]
-    trainer = MeshTrainer(model, bg, world=world, rank=rank, optimizer_step=not args.no_optimizer, fast=not args.reference_ops)
+    trainer = MeshTrainer(model, bg, world=world, rank=rank, optimizer_step=not args.no_optimizer, fast=not args.reference_ops,
+                          native=not (args.no_native or args.reference_ops))
 
     def barrier():
         if world > 1:
@@ -421,7 +423,7 @@ def main():
             "steps": K_, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "P": P, "faces": F, "K": K, "width": W, "height": H, "sh_degree": 3,
-                       "cameras": len(cams), "N_mean": N_mean, "optimizer_step": not args.no_optimizer, "glue": "reference-ops" if args.reference_ops else "fused", "options": args.opt,
+                       "cameras": len(cams), "N_mean": N_mean, "optimizer_step": not args.no_optimizer, "glue": "reference-ops" if args.reference_ops else ("fused, one C call per frame (gms_train_frame)" if not args.no_native else "fused, autograd-driven"), "options": args.opt,
                        "parallelism": f"frame-sharded dp{world}", "l2": "inputs_exceed_l2 (per-step working set > 126 MB)",
                        "frame_algo_bytes": frame_bytes, "frame_hbm_frac": frame_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

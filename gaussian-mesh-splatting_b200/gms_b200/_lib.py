@@ -86,13 +86,24 @@ class AdamArgs(C.Structure):
                 ("eps", C.c_float), ("step", C.c_int32), ("zero_grad", C.c_int32)]
 
 
+class FrameArgs(C.Structure):
+    _fields_ = [("V", C.c_int32), ("F", C.c_int32), ("K", C.c_int32), ("M", C.c_int32),
+                ("vertices", C.c_void_p), ("faces", C.c_void_p), ("alpha_raw", C.c_void_p), ("scale_raw", C.c_void_p),
+                ("features", C.c_void_p), ("opacity_raw", C.c_void_p), ("eps", C.c_float),
+                ("d_vertices", C.c_void_p), ("d_alpha_raw", C.c_void_p), ("d_scale_raw", C.c_void_p),
+                ("d_features", C.c_void_p), ("d_opacity_raw", C.c_void_p),
+                ("settings", RasterSettings), ("gt", C.c_void_p), ("lambda_dssim", C.c_float), ("loss", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("num_rendered", C.POINTER(C.c_int64))]
+
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
 
 # every symbol include/gms_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = ["gms_scratch_bytes", "gms_binning_bytes", "gms_rasterize_forward", "gms_rasterize_backward",
                "gms_mark_visible", "gms_debug_get_views", "gms_debug_unpack", "gms_expand_forward",
                "gms_expand_backward", "gms_last_error", "gms_version", "gms_launch_count", "gms_set_option",
-               "gms_kernel_times", "gms_loss_scratch_bytes", "gms_l1_ssim_loss", "gms_adam_step"]
+               "gms_kernel_times", "gms_loss_scratch_bytes", "gms_l1_ssim_loss", "gms_adam_step",
+               "gms_frame_workspace_bytes", "gms_train_frame"]
 
 _lib = None
 
@@ -132,6 +143,9 @@ def lib():
     L.gms_loss_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     L.gms_l1_ssim_loss.argtypes = [C.POINTER(LossArgs), C.c_void_p]
     L.gms_adam_step.argtypes = [C.POINTER(AdamArgs), C.c_void_p]
+    L.gms_frame_workspace_bytes.restype = C.c_size_t
+    L.gms_frame_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.gms_train_frame.argtypes = [C.POINTER(FrameArgs), ALLOC_FN, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

@@ -46,6 +46,62 @@ def render_frame(model: MeshGaussianModel, cam: Camera, bg: torch.Tensor, fused:
                                                       shs=model.get_features, scales=scales, rotations=rots)
 
 
+class NativeFrame:
+    """One training frame through gms_train_frame: expansion, rasterizer, loss and both backward passes issued from ONE C
+    call on the current stream -- no autograd graph, no per-op Python.  Gradients land in the parameters' preallocated
+    .grad views (FlatAdam's flat buffer); intermediates live in a persistent workspace, rasterizer scratch in grow-only
+    buffers served through the allocation callback."""
+
+    def __init__(self, model: MeshGaussianModel, width: int, height: int, lambda_dssim: float = 0.2):
+        import ctypes as C
+        from . import _lib
+        assert model._features is not None, "NativeFrame needs packed SH features"
+        self.model, self.W, self.H, self.lam = model, int(width), int(height), float(lambda_dssim)
+        dev = model.vertices.device
+        self.dev = dev
+        P = model._scale.shape[0]
+        self.ws = torch.empty(int(_lib.lib().gms_frame_workspace_bytes(P, self.W, self.H)), dtype=torch.uint8, device=dev)
+        self.loss = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.n_rendered = C.c_int64(0)
+        scratch = {}
+        self._scratch = scratch
+
+        def _alloc(user, which, nbytes):        # grow-only, persistent across frames: no allocator traffic in steady state
+            t = scratch.get(int(which))
+            if t is None or t.numel() < nbytes:
+                try:
+                    t = torch.empty(int(nbytes * 1.25) + (1 << 20), dtype=torch.uint8, device=dev)
+                except Exception:
+                    return 0
+                scratch[int(which)] = t
+            return t.data_ptr()
+
+        self._cb = _lib.ALLOC_FN(_alloc)        # closure captures `scratch`/`dev` only (no reference cycle through self)
+
+    def run(self, cam: Camera, gt: torch.Tensor, bg: torch.Tensor) -> torch.Tensor:
+        import ctypes as C
+        from . import _lib
+        m = self.model
+        a = _lib.FrameArgs()
+        a.V, a.F, a.K, a.M = m.vertices.shape[0], m._alpha.shape[0], m._alpha.shape[1], m._features.shape[1]
+        a.vertices, a.faces, a.alpha_raw, a.scale_raw = m.vertices.data_ptr(), m.faces.data_ptr(), m._alpha.data_ptr(), m._scale.data_ptr()
+        a.features, a.opacity_raw, a.eps = m._features.data_ptr(), m._opacity.data_ptr(), m.eps_s0
+        a.d_vertices, a.d_alpha_raw, a.d_scale_raw = m.vertices.grad.data_ptr(), m._alpha.grad.data_ptr(), m._scale.grad.data_ptr()
+        a.d_features, a.d_opacity_raw = m._features.grad.data_ptr(), m._opacity.grad.data_ptr()
+        s = a.settings
+        s.image_height, s.image_width, s.tanfovx, s.tanfovy = self.H, self.W, cam.tanfovx, cam.tanfovy
+        s.bg, s.scale_modifier = bg.data_ptr(), 1.0
+        s.viewmatrix, s.projmatrix, s.campos = cam.world_view_transform.data_ptr(), cam.full_proj_transform.data_ptr(), cam.camera_center.data_ptr()
+        s.sh_degree, s.prefiltered, s.debug, s.antialiasing = m.active_sh_degree, 0, 0, 0
+        a.gt, a.lambda_dssim, a.loss = gt.data_ptr(), self.lam, self.loss.data_ptr()
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        a.num_rendered = C.pointer(self.n_rendered)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().gms_train_frame(C.byref(a), self._cb, None, torch.cuda.current_stream(self.dev).cuda_stream),
+                       "gms_train_frame")
+        return self.loss[0]
+
+
 class MeshTrainer:
     """fwd + loss + bwd (+ gradient all-reduce) + Adam for one frame per rank.
 
@@ -54,11 +110,13 @@ class MeshTrainer:
     fast=False : the reference's op sequence (two-step expansion + getters, ATen loss, torch.optim.Adam)."""
 
     def __init__(self, model: MeshGaussianModel, bg: torch.Tensor, lambda_dssim: float = 0.2, world: int = 1,
-                 rank: int = 0, optimizer_step: bool = True, fast: bool = True):
+                 rank: int = 0, optimizer_step: bool = True, fast: bool = True, native: bool = False):
         self.model, self.bg, self.lambda_dssim = model, bg, lambda_dssim
         self.world, self.rank = world, rank
         self.optimizer_step = optimizer_step
         self.fast = fast
+        self.native = native and fast       # native: the whole frame is one C call (NativeFrame), no autograd
+        self._frame = None
         if fast:
             self.opt = FlatAdam(mesh_model_groups(model), world=world, rank=rank)   # sharded over the ranks when world > 1
             self.flat_grad = self.opt.flat_grad
@@ -81,6 +139,18 @@ class MeshTrainer:
                     p.grad.mul_(1.0 / self.world)
 
     def step(self, cam: Camera, gt: torch.Tensor) -> torch.Tensor:
+        if self.native:
+            if self._frame is None:
+                self._frame = NativeFrame(self.model, cam.image_width, cam.image_height, self.lambda_dssim)
+            loss = self._frame.run(cam, gt, self.bg)
+            from . import rasterizer as _r
+            _r.last_num_rendered = int(self._frame.n_rendered.value)
+            self._all_reduce()
+            if self.optimizer_step:
+                self.opt.step()
+            else:
+                self.opt.zero_grad()
+            return loss
         from . import rasterizer as _r
         _r.DIRECT_SH_GRAD = self.fast      # FlatAdam keeps .grad preallocated and zeroed: write dL/dshs in place
         image, radii, _ = render_frame(self.model, cam, self.bg, fused=self.fast)

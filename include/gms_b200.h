@@ -231,6 +231,31 @@ typedef struct gms_adam_args {
 } gms_adam_args;
 int gms_adam_step(const gms_adam_args* a, void* cuda_stream);
 
+/* One gs_mesh training frame in ONE call (train.py:100-108 + :154-157 of the reference: render + loss + backward +
+ * re-expansion), all launches on `cuda_stream`, no Python / autograd in between:
+ *   expansion fwd (activated scales/rotations) -> sigmoid(opacity) -> rasterizer fwd -> L1+SSIM -> rasterizer bwd ->
+ *   sigmoid bwd -> expansion bwd.
+ * Model tensors are the RAW parameters; gradients are written (d_vertices: accumulated with atomics, keep it zeroed)
+ * into caller buffers, e.g. views of the flat gradient buffer gms_adam_step / the NCCL exchange operate on.
+ * `workspace` holds the per-frame intermediates (gms_frame_workspace_bytes); the rasterizer's scratch still comes
+ * through the allocation callback. */
+typedef struct gms_frame_args {
+    int32_t V, F, K, M;
+    const float* vertices; const int64_t* faces; const float* alpha_raw; const float* scale_raw;
+    const float* features;      /* [P,M,3] packed SH (get_features) */
+    const float* opacity_raw;   /* [P,1] logits */
+    float eps;                  /* eps_s0 */
+    float* d_vertices; float* d_alpha_raw; float* d_scale_raw; float* d_features; float* d_opacity_raw;
+    gms_raster_settings settings;
+    const float* gt;            /* [3,H,W] */
+    float lambda_dssim;
+    float* loss;                /* device [3]: loss, L1, SSIM */
+    void* workspace; size_t workspace_bytes;
+    int64_t* num_rendered;      /* host, optional */
+} gms_frame_args;
+size_t gms_frame_workspace_bytes(int32_t P, int32_t W, int32_t H);
+int gms_train_frame(const gms_frame_args* a, gms_alloc_fn alloc, void* alloc_user, void* cuda_stream);
+
 /* ---- misc ------------------------------------------------------------------------------------- */
 const char* gms_last_error(void);
 const char* gms_version(void);

@@ -81,3 +81,37 @@ def test_fast_trainer_equals_reference_ordered_step():
     assert la[2] < la[0]
     np.testing.assert_allclose(ma._opacity.detach().cpu().numpy(), mb._opacity.detach().cpu().numpy(), rtol=1e-3, atol=2e-3)
     np.testing.assert_allclose(ma._features_dc.detach().cpu().numpy(), mb._features_dc.detach().cpu().numpy(), rtol=1e-3, atol=2e-3)
+
+
+def test_native_frame_equals_autograd_path():
+    """gms_train_frame (one C call for the whole frame) == the autograd fast path: same loss, same gradients, same
+    parameters after a few optimizer steps."""
+    p = scenes.init_mesh_gaussians(*scenes.icosphere(4), K=3, seed=6)
+    cams = [c.to("cuda") for c in scenes.ring_cameras(3, 2.5, 352, 256)]
+    bg = torch.ones(3, device="cuda")
+    gt_model = MeshGaussianModel.from_params(scenes.init_mesh_gaussians(*scenes.icosphere(4), K=3, seed=78), "cuda")
+    with torch.no_grad():
+        gts = [render_frame(gt_model, c, bg)[0].clamp(0, 1).contiguous() for c in cams]
+    ma = MeshGaussianModel.from_params(p, "cuda", packed_features=True)
+    mb = MeshGaussianModel.from_params(p, "cuda", packed_features=True)
+    ta = MeshTrainer(ma, bg, fast=True, native=True, optimizer_step=False)
+    tb = MeshTrainer(mb, bg, fast=True, native=False, optimizer_step=False)
+    # one frame, gradients compared before they are cleared
+    from gms_b200.trainer import NativeFrame
+    fr = NativeFrame(ma, 352, 256)
+    la = fr.run(cams[0], gts[0], bg).item()
+    ga = ta.opt.flat_grad.clone(); ta.opt.zero_grad()
+    from gms_b200 import rasterizer
+    rasterizer.DIRECT_SH_GRAD = True
+    image, _, _ = render_frame(mb, cams[0], bg)
+    lb = losses.fused_training_loss(image, gts[0], 0.2); lb.backward()
+    gb = tb.opt.flat_grad.clone(); tb.opt.zero_grad()
+    assert abs(la - lb.item()) <= 1e-6 * max(1.0, abs(lb.item()))
+    assert (ga - gb).abs().max().item() <= 2e-3 * gb.abs().max().item()
+    # a few full steps
+    ta = MeshTrainer(ma, bg, fast=True, native=True); tb = MeshTrainer(mb, bg, fast=True, native=False)
+    for s in range(4):
+        l1 = ta.step(cams[s % 3], gts[s % 3]).item(); l2 = tb.step(cams[s % 3], gts[s % 3]).item()
+        assert abs(l1 - l2) <= 2e-4 * abs(l2)
+    np.testing.assert_allclose(ma._opacity.detach().cpu().numpy(), mb._opacity.detach().cpu().numpy(), rtol=1e-3, atol=2e-3)
+    np.testing.assert_allclose(ma._features.detach().cpu().numpy(), mb._features.detach().cpu().numpy(), rtol=1e-3, atol=2e-3)
