@@ -350,6 +350,9 @@ def main():
     for b in range(2):
         consumed[b].record(torch.cuda.current_stream(dev))
 
+    loss_host = torch.zeros(1).pin_memory()
+    loss_ready = torch.cuda.Event()
+
     def step_e2e(s):
         ci = shard_cameras(len(cams), s, rank, world)
         b = s & 1
@@ -358,9 +361,10 @@ def main():
         c = cams[ci]
         cb = cam_bufs[b]
         cam = Camera(c.image_width, c.image_height, c.FoVx, c.FoVy, cb[:16].view(4, 4), cb[16:32].view(4, 4), cb[32:35])
-        loss = trainer.step(cam, gt_bufs[b])
+        trainer.step(cam, gt_bufs[b], loss_host=loss_host, loss_ready=loss_ready)
         consumed[b].record(torch.cuda.current_stream(dev))
-        return loss.item()     # device -> host read of the step's result
+        loss_ready.synchronize()          # device -> host read of THIS step's loss (4 bytes into pinned memory), every step;
+        return float(loss_host[0])        # the copy is queued ahead of the optimizer kernels, so Adam overlaps the next launch
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:

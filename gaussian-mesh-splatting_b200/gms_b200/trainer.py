@@ -138,13 +138,21 @@ class MeshTrainer:
                     dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
                     p.grad.mul_(1.0 / self.world)
 
-    def step(self, cam: Camera, gt: torch.Tensor) -> torch.Tensor:
+    def step(self, cam: Camera, gt: torch.Tensor, loss_host: Optional[torch.Tensor] = None,
+             loss_ready: Optional[torch.cuda.Event] = None) -> torch.Tensor:
+        """One optimisation step.  If `loss_host` (pinned) / `loss_ready` are given, the loss is copied to the host right
+        after the backward pass and `loss_ready` is recorded BEFORE the optimizer kernels are queued: a caller that logs
+        the loss every step waits only for the frame, and its next step's launch overhead overlaps the Adam pass."""
         if self.native:
             if self._frame is None:
                 self._frame = NativeFrame(self.model, cam.image_width, cam.image_height, self.lambda_dssim)
             loss = self._frame.run(cam, gt, self.bg)
             from . import rasterizer as _r
             _r.last_num_rendered = int(self._frame.n_rendered.value)
+            if loss_host is not None:
+                loss_host.copy_(loss.reshape(loss_host.shape), non_blocking=True)
+                if loss_ready is not None:
+                    loss_ready.record(torch.cuda.current_stream(loss.device))
             self._all_reduce()
             if self.optimizer_step:
                 self.opt.step()
@@ -156,6 +164,10 @@ class MeshTrainer:
         image, radii, _ = render_frame(self.model, cam, self.bg, fused=self.fast)
         loss = fused_training_loss(image, gt, self.lambda_dssim) if self.fast else training_loss(image, gt, self.lambda_dssim)
         loss.backward()
+        if loss_host is not None:
+            loss_host.copy_(loss.detach().reshape(loss_host.shape), non_blocking=True)
+            if loss_ready is not None:
+                loss_ready.record(torch.cuda.current_stream(loss.device))
         self._all_reduce()
         if self.optimizer_step:
             self.opt.step()

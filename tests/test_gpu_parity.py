@@ -120,7 +120,7 @@ def test_quad_masks_do_not_change_results():
         assert np.abs(a[4][k] - b[4][k]).max() / sc < (5e-3 if k in ('scales', 'rotations') else 2e-4), k   # float atomics: summation order differs
 
 
-@pytest.mark.parametrize("version,tile_order", [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1)])
+@pytest.mark.parametrize("version,tile_order", [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (4, 0), (4, 1)])
 def test_composite_generations_agree_and_match_oracle(version, tile_order):
     """Generation 1 (block-synchronous) and 2 (warp-independent, longest-first tile order) are the same function."""
     S, g = _case(12000, 352, 272, seed=21, extent=1.0, scale_mu=-2.2)
