@@ -388,6 +388,25 @@ def main():
     if sampler:
         sampler.active = False
         sampler.stop()
+    # diagnostics (untimed, reported under e2e.probe): host->device bandwidth of the pinned ground-truth copy, and the
+    # same loop with resident inputs but the per-step loss read kept
+    probe = {}
+    try:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(8):
+            gt_bufs[k & 1].copy_(gts_host[k % len(gts_host)], non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        probe["h2d_gbs"] = 8 * gts_host[0].numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+        def step_read_only(s):
+            ci = shard_cameras(len(cams), s, rank, world)
+            trainer.step(cams_dev[ci], gts[ci], loss_host=loss_host, loss_ready=loss_ready)
+            loss_ready.synchronize()
+        probe["ms_per_step_resident_inputs_with_loss_read"] = timed(step_read_only, min(K_, 50), 0) / min(K_, 50)
+    except Exception as e:  # pragma: no cover
+        probe["error"] = repr(e)
     # per-kernel device time (CUDA events on the launching stream, inside the library), separate pass
     _lib.set_option("time_kernels", 1)
     _lib.kernel_times(reset=True)
@@ -431,7 +450,7 @@ def main():
                        "parallelism": f"frame-sharded dp{world}", "l2": "inputs_exceed_l2 (per-step working set > 126 MB)",
                        "frame_algo_bytes": frame_bytes, "frame_hbm_frac": frame_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / K_},
+                    "ms_per_step": ms_e2e / K_, "probe": probe},
             "gpu_launches": int(launches), "roofline": roof, "kernels": per_kernel,
             "clocks": sampler.summary() if sampler else None}
     if world == 1 and not args.no_cpu_baseline:
