@@ -23,6 +23,9 @@ for p in (ROOT, os.path.join(ROOT, "gaussian-mesh-splatting_b200"), os.path.join
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# NCCL writes its version banner to stdout; the driver expects ONE JSON line there
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -41,6 +44,12 @@ ALGO_BYTES = {  # algorithmic bytes per unit, SURVEY.md section 8(d) / DESIGN.md
     "emit_dups": dict(P=28, N=8), "cub_sort_tiles": dict(N=16), "cub_sort_depth": dict(P=16), "tile_ranges": dict(N=4),
     "cub_scan_tiles": dict(P=12), "ssim_stats": dict(px=3 * (8 + 12)), "ssim_grad": dict(px=3 * (12 + 8 + 4)), "adam": dict(P=53 * 28 + 0),
 }
+
+
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
+# this workload (profiles/r1i_composite_bwd3_ncu_summary.csv, profiles/r1i_composite_ncu_summary.csv); ncu replays the
+# kernel, so these are constants here, not measured inside the timed run.
+NCU_TRAFFIC_BYTES = {("gs_mesh_1M_1080p", "composite_bwd"): 131.51e6 + 17.29e6, ("gs_mesh_1M_1080p", "composite_fwd"): 53.69e6 + 11.74e6}
 
 
 def build_scene(name, seed=0):
@@ -438,7 +447,7 @@ def main():
     if dom:
         a = per_kernel[dom]["gbs"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": per_kernel[dom]["ms"],
+                "traffic": NCU_TRAFFIC_BYTES.get((args.workload, dom)), "peak_source": peak_src, "kernel_ms": per_kernel[dom]["ms"],
                 "algo_bytes_per_launch": per_kernel[dom]["algo_bytes"],
                 "note": "composite kernels are FP32-issue bound (exp + ~50 flops per pixel x splat), not HBM bound; see DESIGN.md"}
     frame_bytes = 1014 * P + 96 * F + 172 * N_mean + 48 * W * H
