@@ -327,3 +327,48 @@ GMS_HD void gms_expand_face_bwd(const gms_expand_args& a, const gms_expand_grads
         }
     }
 }
+
+
+// ---- gs_points pseudo-mesh path: every Gaussian carries its own triangle (v1, v2, v3);
+// PointsGaussianModel.prepare_scaling_rot  games/flat_splatting/scene/points_gaussian_model.py:61-104 and the per-frame
+// call in renderer/gaussian_points_animated_renderer/__init__.py:61-66 (_xyz = triangles[:, 0]).  Forward only: the
+// reference uses it under torch.no_grad() in scripts/render_points_time_animated.py.
+GMS_HD void gms_points_face_fwd(const gms_points_args& a, int i) {
+    const float* t = a.triangles + 9 * (size_t)i;
+    const float* v1 = t; const float* v2 = t + 3; const float* v3 = t + 6;
+    float e2[3], e3[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { e2[k] = v2[k] - v1[k]; e3[k] = v3[k] - v1[k]; }
+    GmsFrame f;                                   // v0 <- r1 (normal), v1 <- r2, v2 <- r3: rotation COLUMNS
+    f.n[0] = e2[1] * e3[2] - e2[2] * e3[1];
+    f.n[1] = e2[2] * e3[0] - e2[0] * e3[2];
+    f.n[2] = e2[0] * e3[1] - e2[1] * e3[0];
+    f.nn = gms_norm3(f.n);
+    const float s2 = gms_norm3(e2) + a.eps;
+    const float inn = 1.0f / (f.nn + a.eps);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { f.v0[k] = f.n[k] * inn; f.v1[k] = e2[k] / s2; }
+    const float d0 = gms_dotv(e3, f.v0), d1 = gms_dotv(e3, f.v1);
+    float u[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) u[k] = e3[k] - d0 * f.v0[k] - d1 * f.v1[k];
+    const float lu = gms_norm3(u) + a.eps;
+#pragma unroll
+    for (int k = 0; k < 3; k++) f.v2[k] = u[k] / lu;
+    const float s3 = gms_dotv(e3, f.v2);
+    float q[4];
+    GmsQuatAux ax;
+    gms_frame_quat(f, q, ax);
+    if (a.xyz) { a.xyz[3 * (size_t)i] = v1[0]; a.xyz[3 * (size_t)i + 1] = v1[1]; a.xyz[3 * (size_t)i + 2] = v1[2]; }
+    if (a.scaling_log) { a.scaling_log[2 * (size_t)i] = logf(fabsf(s2)); a.scaling_log[2 * (size_t)i + 1] = logf(fabsf(s3)); }
+    if (a.scaling_act) {      // get_scaling = cat([eps], exp(_scaling))  (points_gaussian_model.py:106-109)
+        a.scaling_act[3 * (size_t)i] = a.eps;
+        a.scaling_act[3 * (size_t)i + 1] = expf(logf(fabsf(s2)));
+        a.scaling_act[3 * (size_t)i + 2] = expf(logf(fabsf(s3)));
+    }
+    if (a.rotation_raw) { float* o = a.rotation_raw + 4 * (size_t)i; o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3]; }
+    if (a.rotation_act) {
+        const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+        float* o = a.rotation_act + 4 * (size_t)i; o[0] = q[0] / qn; o[1] = q[1] / qn; o[2] = q[2] / qn; o[3] = q[3] / qn;
+    }
+}

@@ -201,3 +201,38 @@ def patch_mesh_model(model):
     model.update_alpha = types.MethodType(update_alpha, model)
     model.prepare_scaling_rot = types.MethodType(prepare_scaling_rot, model)
     return model
+
+
+def points_prepare_scaling_rot(triangles: torch.Tensor, eps: float = 1e-8, activated: bool = False):
+    """gs_points pseudo-mesh: triangles [P,3,3] (one per Gaussian) -> (xyz [P,3] = triangles[:,0], scaling, rotation).
+    activated=False: (_scaling [P,2], _rotation [P,4]) as PointsGaussianModel.prepare_scaling_rot stores them
+    (games/flat_splatting/scene/points_gaussian_model.py:61-104); activated=True: (get_scaling [P,3], get_rotation [P,4]).
+    Forward only (the reference calls it under no_grad, renderer/gaussian_points_animated_renderer/__init__.py:61-66)."""
+    if not triangles.is_cuda:
+        raise RuntimeError("points_prepare_scaling_rot: CUDA tensors required (no CPU path in the product)")
+    t = _f32(triangles.detach())
+    P, dev = t.shape[0], t.device
+    xyz = torch.empty(P, 3, device=dev)
+    sc = torch.empty(P, 3 if activated else 2, device=dev)
+    rot = torch.empty(P, 4, device=dev)
+    a = _lib.PointsArgs()
+    a.P, a.triangles, a.eps, a.xyz = P, t.data_ptr(), float(eps), xyz.data_ptr()
+    if activated:
+        a.scaling_act, a.rotation_act = sc.data_ptr(), rot.data_ptr()
+    else:
+        a.scaling_log, a.rotation_raw = sc.data_ptr(), rot.data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().gms_points_expand_forward(C.byref(a), _stream(dev)), "gms_points_expand_forward")
+    return xyz, sc, rot
+
+
+def patch_points_model(model):
+    """Swap the fused kernel into a reference-style PointsGaussianModel instance (prepare_scaling_rot(triangles=None, eps))."""
+    import types
+
+    def prepare_scaling_rot(self, triangles=None, eps=1e-8):
+        tri = self.triangles if triangles is None else triangles
+        _, self._scaling, self._rotation = points_prepare_scaling_rot(tri, eps, activated=False)
+
+    model.prepare_scaling_rot = types.MethodType(prepare_scaling_rot, model)
+    return model

@@ -195,6 +195,21 @@ typedef struct gms_expand_grads {
 
 int gms_expand_backward(const gms_expand_args* a, const gms_expand_grads* g, void* cuda_stream);
 
+/* gs_points pseudo-mesh path: one triangle per Gaussian -> (xyz = v1, 2 log-scales, quaternion).  Replaces
+ * PointsGaussianModel.prepare_scaling_rot (games/flat_splatting/scene/points_gaussian_model.py:61-104) as called per
+ * frame by renderer/gaussian_points_animated_renderer/__init__.py:61-66.  Forward only (render scripts, no_grad). */
+typedef struct gms_points_args {
+    int32_t P;
+    const float* triangles;      /* [P,3,3] */
+    float eps;                   /* 1e-8 */
+    float* xyz;                  /* [P,3] = triangles[:,0]            (any output may be NULL) */
+    float* scaling_log;          /* [P,2] (pc._scaling) */
+    float* rotation_raw;         /* [P,4] (pc._rotation) */
+    float* scaling_act;          /* [P,3] = (eps, exp(_scaling))      (get_scaling) */
+    float* rotation_act;         /* [P,4] = normalize(_rotation)      (get_rotation) */
+} gms_points_args;
+int gms_points_expand_forward(const gms_points_args* a, void* cuda_stream);
+
 /* ---- training-step glue on the same stream (the callers either side of the path) ---- */
 
 /* L = (1-lambda)*L1 + lambda*(1-SSIM) and dL/dimg in two launches.  Replaces utils/loss_utils.py:17-64 as used by

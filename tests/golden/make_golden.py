@@ -13,6 +13,7 @@ What is pinned (everything the reference ships in Python on or beside the hot pa
   sh_colors.npz        eval_sh + 0.5 clamp (utils/sh_utils.py:57-112; renderer/gaussian_renderer/__init__.py:82-87)
   cov3d.npz            build_scaling_rotation / strip_symmetric (utils/general_utils.py:144-190,
                        scene/gaussian_model.py:27-31)  == --compute_cov3D_python
+  points_model.npz     PointsGaussianModel.prepare_scaling_rot / get_scaling (games/flat_splatting/scene/points_gaussian_model.py:61-109)
   loss.npz             l1_loss / ssim / 0.8*L1 + 0.2*(1-SSIM) and its autograd gradient (utils/loss_utils.py:17-64, train.py:105-107)
   camera.npz           getWorld2View2 / getProjectionMatrix / Camera matrix algebra
                        (utils/graphics_utils.py:22-71, scene/cameras.py:54-57), geom_transform_points
@@ -199,6 +200,30 @@ def quat():
     np.savez_compressed(os.path.join(HERE, "rot_to_quat.npz"), R=R.numpy(), quat=out.numpy())
 
 
+def points():
+    """PointsGaussianModel.prepare_scaling_rot + get_scaling (games/flat_splatting/scene/points_gaussian_model.py:61-109)."""
+    from games.flat_splatting.scene.points_gaussian_model import PointsGaussianModel
+    g = torch.Generator().manual_seed(11)
+    P = 200
+    tri = torch.randn(P, 3, 3, generator=g)
+    tri[:, 1] = tri[:, 0] + 0.2 * torch.randn(P, 3, generator=g)
+    tri[:, 2] = tri[:, 0] + 0.2 * torch.randn(P, 3, generator=g)
+    m = PointsGaussianModel(3)
+    _ones = torch.ones
+    torch.ones = lambda *a, **k: _ones(*a, **{kk: vv for kk, vv in k.items()})
+    m.prepare_scaling_rot(tri)
+    _cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self          # get_scaling builds s0 with .cuda()
+    try:
+        gs = m.get_scaling
+    finally:
+        torch.Tensor.cuda = _cuda
+        torch.ones = _ones
+    np.savez_compressed(os.path.join(HERE, "points_model.npz"), triangles=tri.numpy(), _scaling=m._scaling.numpy(),
+                        _rotation=m._rotation.numpy(), get_scaling=gs.numpy(),
+                        get_rotation=torch.nn.functional.normalize(m._rotation).numpy())
+
+
 def loss():
     g = torch.Generator().manual_seed(8)
     a = torch.rand(3, 45, 70, generator=g, requires_grad=True)
@@ -211,7 +236,7 @@ def loss():
 
 
 if __name__ == "__main__":
-    expansion_mesh(); expansion_multi(); sh_colors(); cov3d(); camera(); quat(); loss()
+    expansion_mesh(); expansion_multi(); sh_colors(); cov3d(); camera(); quat(); loss(); points()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -149,3 +149,16 @@ def test_animated_path_reexpands_from_triangles():
     np.testing.assert_allclose(xyz.detach().cpu().numpy(), oxyz.numpy(), atol=2e-6)
     np.testing.assert_allclose(m._scaling.detach().cpu().numpy(), osl.numpy(), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(m._rotation.detach().cpu().numpy(), orr.numpy(), atol=2e-6)
+
+
+def test_points_pseudomesh_path_matches_reference_golden(golden_dir):
+    """gs_points (renderer/gaussian_points_animated_renderer/__init__.py:61-66): triangles -> xyz / scaling / rotation."""
+    g = np.load(os.path.join(golden_dir, "points_model.npz"))
+    tri = torch.tensor(g["triangles"], device="cuda")
+    xyz, sl, rr = expansion.points_prepare_scaling_rot(tri, activated=False)
+    assert torch.equal(xyz, tri[:, 0])
+    np.testing.assert_allclose(sl.cpu().numpy(), g["_scaling"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(rr.cpu().numpy(), g["_rotation"], atol=2e-6)
+    _, sa, ra = expansion.points_prepare_scaling_rot(tri, activated=True)
+    np.testing.assert_allclose(sa.cpu().numpy(), g["get_scaling"], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(ra.cpu().numpy(), g["get_rotation"], atol=2e-6)

@@ -185,3 +185,21 @@ def test_preprocess_backward_vs_oracle(shim, aa):
     close(o["dm"], ref["dL_dmeans3D"], "means3D"); close(o["dcov"], ref["dL_dcov3D"], "cov3D")
     close(o["dsh"], ref["dL_dsh"], "sh"); close(o["dsc"], ref["dL_dscales"], "scales")
     close(o["drot"], ref["dL_drotations"], "rot"); close(o["dop"], ref["dL_dopacity"].reshape(-1), "opacity")
+
+
+def test_points_pseudomesh_expansion_matches_reference_golden(shim, golden_dir):
+    """gs_points: the product's gms_points_face_fwd (CPU build) against PointsGaussianModel.prepare_scaling_rot / get_scaling."""
+    g = np.load(os.path.join(golden_dir, "points_model.npz"))
+    tri = np.ascontiguousarray(g["triangles"], np.float32)
+    P = tri.shape[0]
+    xyz = np.zeros((P, 3), np.float32); sl = np.zeros((P, 2), np.float32); rr = np.zeros((P, 4), np.float32)
+    sa = np.zeros((P, 3), np.float32); ra = np.zeros((P, 4), np.float32)
+    a = _lib.PointsArgs()
+    a.P, a.triangles, a.eps = P, tri.ctypes.data, 1e-8
+    a.xyz, a.scaling_log, a.rotation_raw, a.scaling_act, a.rotation_act = [x.ctypes.data for x in (xyz, sl, rr, sa, ra)]
+    assert shim.shim_points_expand_forward(C.byref(a)) == 0
+    np.testing.assert_array_equal(xyz, tri[:, 0])
+    np.testing.assert_allclose(sl, g["_scaling"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(rr, g["_rotation"], atol=2e-6)
+    np.testing.assert_allclose(sa, g["get_scaling"], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(ra, g["get_rotation"], atol=2e-6)
