@@ -42,7 +42,7 @@ ALGO_BYTES = {  # algorithmic bytes per unit, SURVEY.md section 8(d) / DESIGN.md
     "preprocess_fwd": dict(P=311), "preprocess_bwd": dict(P=563),
     "expand_fwd": dict(P=56, F=60), "expand_bwd": dict(P=56, F=36),
     "emit_dups": dict(P=28, N=8), "cub_sort_tiles": dict(N=16), "cub_sort_depth": dict(P=16), "tile_ranges": dict(N=4),
-    "cub_scan_tiles": dict(P=12), "ssim_stats": dict(px=3 * (8 + 12)), "ssim_grad": dict(px=3 * (12 + 8 + 4)), "adam": dict(P=53 * 28 + 0),
+    "cub_scan_tiles": dict(P=12), "ssim_stats": dict(px=3 * (8 + 12)), "ssim_grad": dict(px=3 * (12 + 8 + 4)), "adam": dict(P=53 * 32),   # p,g,m,v read + p,m,v written + g zeroed = 32 B/parameter
 }
 
 

@@ -81,6 +81,10 @@ class NativeFrame:
     def run(self, cam: Camera, gt: torch.Tensor, bg: torch.Tensor) -> torch.Tensor:
         import ctypes as C
         from . import _lib
+        if int(cam.image_width) != self.W or int(cam.image_height) != self.H or tuple(gt.shape[-2:]) != (self.H, self.W):
+            raise ValueError(f"NativeFrame was sized for {self.W}x{self.H}; got a {cam.image_width}x{cam.image_height} camera")
+        if not gt.is_contiguous() or gt.dtype != torch.float32:
+            gt = gt.contiguous().float()
         m = self.model
         a = _lib.FrameArgs()
         a.V, a.F, a.K, a.M = m.vertices.shape[0], m._alpha.shape[0], m._alpha.shape[1], m._features.shape[1]
@@ -160,10 +164,14 @@ class MeshTrainer:
                 self.opt.zero_grad()
             return loss
         from . import rasterizer as _r
+        prev = _r.DIRECT_SH_GRAD
         _r.DIRECT_SH_GRAD = self.fast      # FlatAdam keeps .grad preallocated and zeroed: write dL/dshs in place
-        image, radii, _ = render_frame(self.model, cam, self.bg, fused=self.fast)
-        loss = fused_training_loss(image, gt, self.lambda_dssim) if self.fast else training_loss(image, gt, self.lambda_dssim)
-        loss.backward()
+        try:
+            image, radii, _ = render_frame(self.model, cam, self.bg, fused=self.fast)
+            loss = fused_training_loss(image, gt, self.lambda_dssim) if self.fast else training_loss(image, gt, self.lambda_dssim)
+            loss.backward()
+        finally:
+            _r.DIRECT_SH_GRAD = prev       # never leak the in-place mode to other users of the rasterizer
         if loss_host is not None:
             loss_host.copy_(loss.detach().reshape(loss_host.shape), non_blocking=True)
             if loss_ready is not None:
