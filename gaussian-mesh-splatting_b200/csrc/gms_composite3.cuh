@@ -184,7 +184,9 @@ struct GmsSlab3B {
     float part[GMS_WB][12];
 };
 
-template <int MINB>
+// DEPTH = false: no loss on the inverse-depth image (train.py never puts one): the depth channel of the recurrence and its
+// moment sum are compiled out.
+template <int MINB, bool DEPTH>
 __global__ void __launch_bounds__(GMS_CB, MINB)
 k_composite_bwd3(const int2* __restrict__ ranges, const int* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
                  const float4* __restrict__ recs, int W, int H, int gx, const float* __restrict__ bg,
@@ -277,17 +279,19 @@ k_composite_bwd3(const int2* __restrict__ ranges, const int* __restrict__ tile_o
             f2 dLa = f2mul(f2fma(Br, neg1, cr), dpr);
             dLa = f2fma(f2fma(Bg, neg1, cg), dpg, dLa);
             dLa = f2fma(f2fma(Bb, neg1, cb), dpb, dLa);
-            dLa = f2fma(f2fma(Bd, neg1, cd), dpd, dLa);
+            if (DEPTH) dLa = f2fma(f2fma(Bd, neg1, cd), dpd, dLa);
             // advance "behind": B <- alpha*c + (1-alpha)*B
             Br = f2fma(alpha, cr, f2mul(oma, Br)); Bg = f2fma(alpha, cg, f2mul(oma, Bg));
-            Bb = f2fma(alpha, cb, f2mul(oma, Bb)); Bd = f2fma(alpha, cd, f2mul(oma, Bd));
+            Bb = f2fma(alpha, cb, f2mul(oma, Bb));
+            if (DEPTH) Bd = f2fma(alpha, cd, f2mul(oma, Bd));
             dLa = f2mul(dLa, T);
             dLa = f2fma(f2mul(nTfin, inv), bgdot, dLa);
             f2 q = f2mul(dLa, G);
             q.x = v0 ? q.x : 0.f; q.y = v1 ? q.y : 0.f;
             const f2 qx = f2mul(q, dx), qy = f2mul(q, dy);
             const f2 pxx = f2mul(qx, dx), pxy = f2mul(qx, dy), pyy = f2mul(qy, dy);
-            const f2 wr = f2mul(w, dpr), wg = f2mul(w, dpg), wb = f2mul(w, dpb), wd = f2mul(w, dpd);
+            const f2 wr = f2mul(w, dpr), wg = f2mul(w, dpg), wb = f2mul(w, dpb);
+            const f2 wd = DEPTH ? f2mul(w, dpd) : make_float2(0.f, 0.f);
             float v[10];
             v[0] = qx.x + qx.y; v[1] = qy.x + qy.y; v[2] = pxx.x + pxx.y; v[3] = pxy.x + pxy.y; v[4] = pyy.x + pyy.y;
             v[5] = q.x + q.y; v[6] = wr.x + wr.y; v[7] = wg.x + wg.y; v[8] = wb.x + wb.y; v[9] = wd.x + wd.y;

@@ -171,6 +171,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.present = (shs is not None, col is not None, sc is not None, rot is not None, cov is not None)
         ctx.save_for_backward(m3, op if op is not None else torch.empty(0, device=device), shs, col, sc, rot, cov, radii)
         ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)     # an unused inverse-depth output arrives as None -> depth channel compiled out
         return color, radii, invdepth
 
     @staticmethod
@@ -187,6 +188,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         b = ctx.scratch.bufs
         saved.geom = _ptr(b.get(_lib.BUF_GEOM)); saved.binning = _ptr(b.get(_lib.BUF_BINNING)); saved.image = _ptr(b.get(_lib.BUF_IMAGE))
         saved.num_rendered = ctx.num_rendered
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((3, int(rs.image_height), int(rs.image_width)), dtype=torch.float32, device=device)
         gcol = _dev_f32(grad_out_color, device)
         gdep = None if grad_out_depth is None else _dev_f32(grad_out_depth, device)
         e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
