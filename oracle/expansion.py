@@ -27,51 +27,70 @@ def update_alpha(_alpha, vertices, faces):
     return alpha, triangles, xyz.reshape(-1, 3)
 
 
-def _dot(v, u):
-    return (v * u).sum(dim=-1, keepdim=True)
+def _rowdot(a, b):
+    return torch.sum(a * b, dim=-1, keepdim=True)
+
+
+def _unit(v, eps):
+    """v / (|v| + eps) and the norm itself."""
+    n = torch.linalg.vector_norm(v, dim=-1, keepdim=True)
+    return v / (n + eps), n
 
 
 def face_frames(triangles, eps=EPS_S0):
-    """-> per-face rotation rows (v0,v1,v2) [F,3,3] and scales (s0,s1,s2) [F,3]."""
-    t0, t1, t2 = triangles[:, 0], triangles[:, 1], triangles[:, 2]
-    normals = torch.linalg.cross(t1 - t0, t2 - t0, dim=1)
-    v0 = normals / (torch.linalg.vector_norm(normals, dim=-1, keepdim=True) + eps)
-    means = torch.mean(triangles, dim=1)
-    v1 = t1 - means
-    v1_norm = torch.linalg.vector_norm(v1, dim=-1, keepdim=True) + eps
-    v1 = v1 / v1_norm
-    v2_init = t2 - means
-    v2 = v2_init - _dot(v2_init, v0) * v0 - _dot(v2_init, v1) * v1
-    v2 = v2 / (torch.linalg.vector_norm(v2, dim=-1, keepdim=True) + eps)
-    s1 = v1_norm / 2.0
-    s2 = _dot(v2_init, v2) / 2.0
-    s0 = eps * torch.ones_like(s1)
-    return torch.stack((v0, v1, v2), dim=1), torch.cat((s0, s1, s2), dim=1)
+    """Per-face orthonormal frame and in-plane half extents.
+    -> rows [F,3,3] = (unit normal, unit centroid->corner1, Gram-Schmidt of centroid->corner2), scales [F,3] = (eps, s1, s2)."""
+    p0, p1, p2 = triangles.unbind(dim=1)
+    normal_hat, _ = _unit(torch.linalg.cross(p1 - p0, p2 - p0, dim=1), eps)
+    centroid = triangles.mean(dim=1)
+    arm1 = p1 - centroid
+    len1 = torch.linalg.vector_norm(arm1, dim=-1, keepdim=True) + eps
+    axis1 = arm1 / len1
+    arm2 = p2 - centroid
+    resid = arm2 - _rowdot(arm2, normal_hat) * normal_hat - _rowdot(arm2, axis1) * axis1
+    axis2, _ = _unit(resid, eps)
+    half1 = len1 / 2.0
+    half2 = _rowdot(arm2, axis2) / 2.0
+    thin = torch.full_like(half1, eps)
+    return torch.stack((normal_hat, axis1, axis2), dim=1), torch.cat((thin, half1, half2), dim=1)
 
 
-def _sqrt_positive_part(x):
-    ret = torch.zeros_like(x)
-    m = x > 0
-    ret[m] = torch.sqrt(x[m])
-    return ret
+# candidate numerators of the quaternion, one row per choice of the dominant component (w, x, y, z);
+# entries: ('d', k) -> squared magnitude k, (+1/-1, (a, b), (c, d)) -> m[a][b] +/- m[c][d]
+_CAND = (
+    (('d', 0), (-1, (2, 1), (1, 2)), (-1, (0, 2), (2, 0)), (-1, (1, 0), (0, 1))),
+    ((-1, (2, 1), (1, 2)), ('d', 1), (+1, (1, 0), (0, 1)), (+1, (0, 2), (2, 0))),
+    ((-1, (0, 2), (2, 0)), (+1, (1, 0), (0, 1)), ('d', 2), (+1, (1, 2), (2, 1))),
+    ((-1, (1, 0), (0, 1)), (+1, (2, 0), (0, 2)), (+1, (2, 1), (1, 2)), ('d', 3)),
+)
 
 
 def rot_to_quat(rot):
-    """pytorch3d matrix_to_quaternion as restated in utils/general_utils.py:43-96; rot [...,3,3]."""
-    m = rot.reshape(-1, 9)
-    m00, m01, m02, m10, m11, m12, m20, m21, m22 = [m[:, i] for i in range(9)]
-    q_abs = _sqrt_positive_part(torch.stack([1.0 + m00 + m11 + m22, 1.0 + m00 - m11 - m22,
-                                             1.0 - m00 + m11 - m22, 1.0 - m00 - m11 + m22], dim=-1))
-    cand = torch.stack([
-        torch.stack([q_abs[:, 0] ** 2, m21 - m12, m02 - m20, m10 - m01], dim=-1),
-        torch.stack([m21 - m12, q_abs[:, 1] ** 2, m10 + m01, m02 + m20], dim=-1),
-        torch.stack([m02 - m20, m10 + m01, q_abs[:, 2] ** 2, m12 + m21], dim=-1),
-        torch.stack([m10 - m01, m20 + m02, m21 + m12, q_abs[:, 3] ** 2], dim=-1)], dim=-2)
-    flr = torch.tensor(0.1, dtype=q_abs.dtype)
-    cand = cand / (2.0 * q_abs[..., None].max(flr))
-    idx = q_abs.argmax(dim=-1)
-    out = cand[torch.arange(cand.shape[0]), idx]
-    return torch.where(out[:, 0:1] < 0, -out, out)
+    """Rotation matrices [...,3,3] -> quaternions (w,x,y,z), w >= 0: the pytorch3d construction the reference uses
+    (utils/general_utils.py:43-96): four candidate magnitudes sqrt(max(0, 1 +- m00 +- m11 +- m22)), take the largest,
+    divide its numerator row by 2*max(|q|, 0.1)."""
+    m = rot.reshape(-1, 3, 3)
+    d0, d1, d2 = m[:, 0, 0], m[:, 1, 1], m[:, 2, 2]
+    arg = torch.stack((1.0 + d0 + d1 + d2, 1.0 + d0 - d1 - d2, 1.0 - d0 + d1 - d2, 1.0 - d0 - d1 + d2), dim=-1)
+    mag = torch.zeros_like(arg)
+    pos = arg > 0
+    mag[pos] = torch.sqrt(arg[pos])
+    rows = []
+    for spec in _CAND:
+        ent = []
+        for e in spec:
+            if e[0] == 'd':
+                ent.append(mag[:, e[1]] ** 2)
+            else:
+                sgn, (a, b), (c, d) = e
+                ent.append(m[:, a, b] + m[:, c, d] if sgn > 0 else m[:, a, b] - m[:, c, d])
+        rows.append(torch.stack(ent, dim=-1))
+    table = torch.stack(rows, dim=-2)                                           # [F,4,4]
+    floor = torch.tensor(0.1, dtype=mag.dtype)
+    table = table / (2.0 * mag[..., None].max(floor))
+    pick = mag.argmax(dim=-1)
+    q = table[torch.arange(table.shape[0]), pick]
+    return torch.where(q[:, :1] < 0, -q, q)
 
 
 def prepare_scaling_rot(triangles, _scale, K, eps=EPS_S0):
