@@ -372,3 +372,25 @@ GMS_HD void gms_points_face_fwd(const gms_points_args& a, int i) {
         float* o = a.rotation_act + 4 * (size_t)i; o[0] = q[0] / qn; o[1] = q[1] / qn; o[2] = q[2] / qn; o[3] = q[3] / qn;
     }
 }
+
+// PointsGaussianModel.prepare_vertices (games/flat_splatting/scene/points_gaussian_model.py:28-59): pseudo-mesh triangle of
+// one flat Gaussian.  scales = (eps, exp(_scaling[-2]), exp(_scaling[-1])) (:106-109); R = build_rotation(_rotation)
+// (utils/general_utils.py:158-179, normalises q); arms along R's 2nd and 3rd COLUMNS (R.transpose(-2,-1)[:, 1|2]);
+// the longer arm becomes v2 (mask = s_2 > s_3, :43-52).
+GMS_HD void gms_points_vertices_fwd(const gms_points_vertices_args& a, int i) {
+    const float* c = a.xyz + 3 * (size_t)i;
+    const float* sl = a.scaling_log + (size_t)a.scaling_cols * i + (a.scaling_cols - 2);
+    const float* qr = a.rotation_raw + 4 * (size_t)i;
+    const float s2 = expf(sl[0]), s3 = expf(sl[1]);
+    const float nrm = sqrtf(qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2] + qr[3] * qr[3]);
+    const float r = qr[0] / nrm, x = qr[1] / nrm, y = qr[2] / nrm, z = qr[3] / nrm;
+    const float ax2[3] = {2.0f * (x * y - r * z), 1.0f - 2.0f * (x * x + z * z), 2.0f * (y * z + r * x)};
+    const float ax3[3] = {2.0f * (x * z + r * y), 2.0f * (y * z - r * x), 1.0f - 2.0f * (x * x + y * y)};
+    float p2[3], p3[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { p2[k] = c[k] + s2 * ax2[k]; p3[k] = c[k] + s3 * ax3[k]; }
+    const bool keep = s2 > s3;
+    float* t = a.triangles + 9 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { t[k] = c[k]; t[3 + k] = keep ? p2[k] : p3[k]; t[6 + k] = keep ? p3[k] : p2[k]; }
+}

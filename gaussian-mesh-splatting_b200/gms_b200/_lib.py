@@ -79,6 +79,12 @@ class PointsArgs(C.Structure):
                 ("rotation_act", C.c_void_p)]
 
 
+class PointsVerticesArgs(C.Structure):
+    """struct gms_points_vertices_args"""
+    _fields_ = [("P", C.c_int32), ("xyz", C.c_void_p), ("scaling_log", C.c_void_p), ("scaling_cols", C.c_int32),
+                ("rotation_raw", C.c_void_p), ("triangles", C.c_void_p)]
+
+
 class LossArgs(C.Structure):
     _fields_ = [("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("img", C.c_void_p), ("gt", C.c_void_p),
                 ("lambda_dssim", C.c_float), ("dL_dloss", C.c_void_p), ("loss", C.c_void_p), ("dL_dimg", C.c_void_p),
@@ -109,7 +115,8 @@ ABI_SYMBOLS = ["gms_scratch_bytes", "gms_binning_bytes", "gms_rasterize_forward"
                "gms_mark_visible", "gms_debug_get_views", "gms_debug_unpack", "gms_expand_forward",
                "gms_expand_backward", "gms_last_error", "gms_version", "gms_launch_count", "gms_set_option",
                "gms_kernel_times", "gms_loss_scratch_bytes", "gms_l1_ssim_loss", "gms_adam_step",
-               "gms_frame_workspace_bytes", "gms_train_frame", "gms_points_expand_forward"]
+               "gms_frame_workspace_bytes", "gms_train_frame", "gms_points_expand_forward",
+               "gms_points_prepare_vertices"]
 
 _lib = None
 
@@ -150,6 +157,7 @@ def lib():
     L.gms_l1_ssim_loss.argtypes = [C.POINTER(LossArgs), C.c_void_p]
     L.gms_adam_step.argtypes = [C.POINTER(AdamArgs), C.c_void_p]
     L.gms_points_expand_forward.argtypes = [C.POINTER(PointsArgs), C.c_void_p]
+    L.gms_points_prepare_vertices.argtypes = [C.POINTER(PointsVerticesArgs), C.c_void_p]
     L.gms_frame_workspace_bytes.restype = C.c_size_t
     L.gms_frame_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.gms_train_frame.argtypes = [C.POINTER(FrameArgs), ALLOC_FN, C.c_void_p, C.c_void_p]

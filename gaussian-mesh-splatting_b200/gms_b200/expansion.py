@@ -226,13 +226,39 @@ def points_prepare_scaling_rot(triangles: torch.Tensor, eps: float = 1e-8, activ
     return xyz, sc, rot
 
 
+def points_prepare_vertices(xyz: torch.Tensor, _scaling: torch.Tensor, _rotation: torch.Tensor) -> torch.Tensor:
+    """gs_points: flat Gaussians -> pseudo-mesh triangles [P,3,3] (v1 = xyz; v2, v3 = xyz + exp(log-scale) * rotation axis,
+    the longer arm first).  PointsGaussianModel.prepare_vertices, games/flat_splatting/scene/points_gaussian_model.py:28-59.
+    `_scaling` is [P,2] or [P,3] (the last two columns are used, as get_scaling :106-109 does); `_rotation` is the raw
+    (w,x,y,z) parameter (normalised inside, utils/general_utils.py:158-161).  Forward only."""
+    if not xyz.is_cuda:
+        raise RuntimeError("points_prepare_vertices: CUDA tensors required (no CPU path in the product)")
+    x, sc, q = _f32(xyz.detach()), _f32(_scaling.detach()), _f32(_rotation.detach())
+    P, dev = x.shape[0], x.device
+    if sc.dim() != 2 or sc.shape[0] != P or sc.shape[1] not in (2, 3) or tuple(q.shape) != (P, 4) or tuple(x.shape) != (P, 3):
+        raise ValueError("points_prepare_vertices: expected xyz [P,3], _scaling [P,2|3], _rotation [P,4]")
+    tri = torch.empty(P, 3, 3, device=dev)
+    a = _lib.PointsVerticesArgs()
+    a.P, a.xyz, a.scaling_log, a.scaling_cols = P, x.data_ptr(), sc.data_ptr(), sc.shape[1]
+    a.rotation_raw, a.triangles = q.data_ptr(), tri.data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().gms_points_prepare_vertices(C.byref(a), _stream(dev)), "gms_points_prepare_vertices")
+    return tri
+
+
 def patch_points_model(model):
-    """Swap the fused kernel into a reference-style PointsGaussianModel instance (prepare_scaling_rot(triangles=None, eps))."""
+    """Swap the fused kernels into a reference-style PointsGaussianModel instance: prepare_vertices() and
+    prepare_scaling_rot(triangles=None, eps)."""
     import types
 
     def prepare_scaling_rot(self, triangles=None, eps=1e-8):
         tri = self.triangles if triangles is None else triangles
         _, self._scaling, self._rotation = points_prepare_scaling_rot(tri, eps, activated=False)
 
+    def prepare_vertices(self):
+        self.triangles = points_prepare_vertices(self._xyz, self._scaling, self._rotation)
+        self.v1, self.v2, self.v3 = self.triangles.unbind(dim=1)
+
     model.prepare_scaling_rot = types.MethodType(prepare_scaling_rot, model)
+    model.prepare_vertices = types.MethodType(prepare_vertices, model)
     return model

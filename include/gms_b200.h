@@ -210,6 +210,20 @@ typedef struct gms_points_args {
 } gms_points_args;
 int gms_points_expand_forward(const gms_points_args* a, void* cuda_stream);
 
+/* gs_points, the other direction: every flat Gaussian -> its pseudo-mesh triangle (v1 = xyz, v2/v3 = xyz + s*axis, the
+ * longer arm first).  Replaces PointsGaussianModel.prepare_vertices (games/flat_splatting/scene/points_gaussian_model.py:
+ * 28-59, with get_scaling :106-109 and build_rotation utils/general_utils.py:158-179), run once when a trained gs_flat
+ * model is loaded for editing (scripts/render_points_time_animated.py).  Forward only. */
+typedef struct gms_points_vertices_args {
+    int32_t P;
+    const float* xyz;            /* [P,3]  pc._xyz */
+    const float* scaling_log;    /* [P,scaling_cols]  pc._scaling; the LAST two columns are the in-plane log-scales */
+    int32_t scaling_cols;        /* 2 (gs_points) or 3 (a gs_flat checkpoint) */
+    const float* rotation_raw;   /* [P,4]  pc._rotation (w,x,y,z), not normalised */
+    float* triangles;            /* out [P,3,3] */
+} gms_points_vertices_args;
+int gms_points_prepare_vertices(const gms_points_vertices_args* a, void* cuda_stream);
+
 /* ---- training-step glue on the same stream (the callers either side of the path) ---- */
 
 /* L = (1-lambda)*L1 + lambda*(1-SSIM) and dL/dimg in two launches.  Replaces utils/loss_utils.py:17-64 as used by

@@ -120,3 +120,39 @@ def expand_multi(vertices_list, faces_list, alpha_list, scale_list, eps=EPS_S0):
     """gaussian_multi_mesh_model.py:99-119,121-174: per-mesh expansion, concatenated."""
     outs = [expand(v, f, a, s, eps)[:3] for v, f, a, s in zip(vertices_list, faces_list, alpha_list, scale_list)]
     return tuple(torch.cat([o[i] for o in outs]) for i in range(3))
+
+
+# ---- gs_points pseudo-mesh (games/flat_splatting/scene/points_gaussian_model.py) ----
+
+def points_prepare_vertices(xyz, _scaling, _rotation):
+    """Flat Gaussians -> their pseudo-mesh triangles [P,3,3]  (points_gaussian_model.py:28-59; get_scaling :106-109;
+    build_rotation utils/general_utils.py:158-179)."""
+    ext = torch.exp(_scaling[:, -2:])
+    q = _rotation / torch.sqrt((_rotation * _rotation).sum(dim=1, keepdim=True))
+    w, x, y, z = q.unbind(dim=1)
+    axis_b = torch.stack((2 * (x * y - w * z), 1 - 2 * (x * x + z * z), 2 * (y * z + w * x)), dim=1)   # column 1 of R
+    axis_c = torch.stack((2 * (x * z + w * y), 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)), dim=1)   # column 2 of R
+    tip_b = xyz + ext[:, :1] * axis_b
+    tip_c = xyz + ext[:, 1:] * axis_c
+    first = (ext[:, 0] > ext[:, 1])[:, None]
+    return torch.stack((xyz, torch.where(first, tip_b, tip_c), torch.where(first, tip_c, tip_b)), dim=1)
+
+
+def points_prepare_scaling_rot(triangles, eps=1e-8):
+    """Pseudo-mesh triangles -> (_scaling [P,2], _rotation [P,4])  (points_gaussian_model.py:61-104)."""
+    apex, b, c = triangles.unbind(dim=1)
+    e_b, e_c = b - apex, c - apex
+    n_hat, _ = _unit(torch.linalg.cross(e_b, e_c, dim=1), eps)
+    len_b = torch.linalg.vector_norm(e_b, dim=-1, keepdim=True) + eps
+    u_b = e_b / len_b
+    u_c, _ = _unit(e_c - _rowdot(e_c, n_hat) * n_hat - _rowdot(e_c, u_b) * u_b, eps)
+    len_c = _rowdot(e_c, u_c)
+    scaling = torch.log(torch.cat((len_b, len_c), dim=1).abs())
+    rot = torch.stack((n_hat, u_b, u_c), dim=1).transpose(-2, -1)
+    return scaling, rot_to_quat(rot)
+
+
+def points_get_scaling(_scaling, eps=1e-8):
+    """get_scaling = (eps, exp(last two log-scales))  (points_gaussian_model.py:106-109)."""
+    return torch.cat((torch.full_like(_scaling[:, :1], eps), torch.exp(_scaling[:, -2:])), dim=1)
+

@@ -13,7 +13,8 @@ What is pinned (everything the reference ships in Python on or beside the hot pa
   sh_colors.npz        eval_sh + 0.5 clamp (utils/sh_utils.py:57-112; renderer/gaussian_renderer/__init__.py:82-87)
   cov3d.npz            build_scaling_rotation / strip_symmetric (utils/general_utils.py:144-190,
                        scene/gaussian_model.py:27-31)  == --compute_cov3D_python
-  points_model.npz     PointsGaussianModel.prepare_scaling_rot / get_scaling (games/flat_splatting/scene/points_gaussian_model.py:61-109)
+  points_model.npz     PointsGaussianModel.prepare_vertices / prepare_scaling_rot / get_scaling
+                       (games/flat_splatting/scene/points_gaussian_model.py:28-109)
   loss.npz             l1_loss / ssim / 0.8*L1 + 0.2*(1-SSIM) and its autograd gradient (utils/loss_utils.py:17-64, train.py:105-107)
   camera.npz           getWorld2View2 / getProjectionMatrix / Camera matrix algebra
                        (utils/graphics_utils.py:22-71, scene/cameras.py:54-57), geom_transform_points
@@ -219,9 +220,26 @@ def points():
     finally:
         torch.Tensor.cuda = _cuda
         torch.ones = _ones
+    # prepare_vertices (:28-59) on an independent flat-Gaussian state: raw (unnormalised) quaternions, both orders of the
+    # two in-plane scales, one tie (mask = s_2 > s_3 is False on equality)
+    v = PointsGaussianModel(3)
+    v._xyz = torch.randn(P, 3, generator=g)
+    sl = -2.0 + 0.7 * torch.randn(P, 2, generator=g)
+    sl[3, 1] = sl[3, 0]
+    v._scaling = sl
+    v._rotation = torch.randn(P, 4, generator=g) * (0.5 + torch.rand(P, 1, generator=g))
+    torch.ones = lambda *a, **k: _ones(*a, **{kk: vv for kk, vv in k.items()})
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        v.prepare_vertices()
+    finally:
+        torch.Tensor.cuda = _cuda
+        torch.ones = _ones
     np.savez_compressed(os.path.join(HERE, "points_model.npz"), triangles=tri.numpy(), _scaling=m._scaling.numpy(),
                         _rotation=m._rotation.numpy(), get_scaling=gs.numpy(),
-                        get_rotation=torch.nn.functional.normalize(m._rotation).numpy())
+                        get_rotation=torch.nn.functional.normalize(m._rotation).numpy(),
+                        pv_xyz=v._xyz.numpy(), pv_scaling=v._scaling.numpy(), pv_rotation=v._rotation.numpy(),
+                        pv_triangles=v.triangles.numpy())
 
 
 def loss():

@@ -24,6 +24,11 @@ int shim_points_expand_forward(const gms_points_args* a) {
     return 0;
 }
 
+int shim_points_prepare_vertices(const gms_points_vertices_args* a) {
+    for (int i = 0; i < a->P; i++) gms_points_vertices_fwd(*a, i);
+    return 0;
+}
+
 // stock-layout outputs; mirrors the glue of k_preprocess_fwd
 int shim_preprocess_forward(int P, int D, int M, int W, int H, float tanfovx, float tanfovy, float mod, int aa,
                             const float* means, const float* scales, const float* rots, const float* cov_pre,

@@ -163,3 +163,34 @@ def test_points_pseudomesh_path_matches_reference_golden(golden_dir):
     # s3 = (v3 - v1) . r3 is a cancellation result for near-collinear triangles: FMA contraction on the GPU moves it by ~1e-7 abs
     np.testing.assert_allclose(sa.cpu().numpy(), g["get_scaling"], rtol=1e-4, atol=1e-7)
     np.testing.assert_allclose(ra.cpu().numpy(), g["get_rotation"], atol=2e-6)
+
+
+def test_points_prepare_vertices_matches_golden_and_oracle(golden_dir):
+    """gs_points prepare_vertices (games/flat_splatting/scene/points_gaussian_model.py:28-59) on the GPU: reference golden
+    vector, the oracle on a larger random state, and the patched-model round trip prepare_vertices -> prepare_scaling_rot."""
+    from oracle import expansion as oexp
+    g = np.load(os.path.join(golden_dir, "points_model.npz"))
+    tri = expansion.points_prepare_vertices(torch.tensor(g["pv_xyz"], device="cuda"),
+                                            torch.tensor(g["pv_scaling"], device="cuda"),
+                                            torch.tensor(g["pv_rotation"], device="cuda"))
+    np.testing.assert_allclose(tri.cpu().numpy(), g["pv_triangles"], rtol=0, atol=1e-6)
+    gen = torch.Generator().manual_seed(3)
+    P = 50_001
+    xyz = torch.randn(P, 3, generator=gen); sl = -3.0 + torch.randn(P, 3, generator=gen)
+    q = torch.randn(P, 4, generator=gen) * 3.0
+    want = oexp.points_prepare_vertices(xyz, sl, q)
+    got = expansion.points_prepare_vertices(xyz.cuda(), sl.cuda(), q.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=0, atol=2e-6)
+
+    class _PM:            # the attributes the reference's PointsGaussianModel methods touch
+        pass
+    m = _PM(); m._xyz, m._scaling, m._rotation = xyz.cuda(), sl.cuda(), q.cuda()
+    expansion.patch_points_model(m)
+    m.prepare_vertices()
+    assert torch.equal(m.triangles, got) and torch.equal(m.v1, m._xyz)
+    m.prepare_scaling_rot()
+    osl, _ = oexp.points_prepare_scaling_rot(want)
+    np.testing.assert_allclose(m._scaling.cpu().numpy(), osl.numpy(), rtol=0, atol=1e-4)
+    longer_first = torch.sort(sl[:, 1:], dim=1, descending=True).values
+    np.testing.assert_allclose(m._scaling.cpu().numpy(), longer_first.numpy(), atol=1e-4)
+

@@ -203,3 +203,23 @@ def test_points_pseudomesh_expansion_matches_reference_golden(shim, golden_dir):
     np.testing.assert_allclose(rr, g["_rotation"], atol=2e-6)
     np.testing.assert_allclose(sa, g["get_scaling"], rtol=1e-5, atol=1e-12)
     np.testing.assert_allclose(ra, g["get_rotation"], atol=2e-6)
+
+
+def test_points_prepare_vertices_matches_reference_golden(shim, golden_dir):
+    """gs_points: the product's gms_points_vertices_fwd (CPU build) against PointsGaussianModel.prepare_vertices
+    (games/flat_splatting/scene/points_gaussian_model.py:28-59), with [P,2] and [P,3] log-scale layouts."""
+    g = np.load(os.path.join(golden_dir, "points_model.npz"))
+    xyz = np.ascontiguousarray(g["pv_xyz"], np.float32); q = np.ascontiguousarray(g["pv_rotation"], np.float32)
+    P = xyz.shape[0]
+    for cols in (2, 3):
+        sl = np.ascontiguousarray(g["pv_scaling"], np.float32)
+        if cols == 3:
+            sl = np.ascontiguousarray(np.concatenate([np.full((P, 1), -18.0, np.float32), sl], axis=1))
+        tri = np.zeros((P, 3, 3), np.float32)
+        a = _lib.PointsVerticesArgs()
+        a.P, a.xyz, a.scaling_log, a.scaling_cols = P, xyz.ctypes.data, sl.ctypes.data, cols
+        a.rotation_raw, a.triangles = q.ctypes.data, tri.ctypes.data
+        assert shim.shim_points_prepare_vertices(C.byref(a)) == 0
+        np.testing.assert_array_equal(tri[:, 0], xyz)
+        np.testing.assert_allclose(tri, g["pv_triangles"], rtol=0, atol=1e-6)
+

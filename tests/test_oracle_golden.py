@@ -133,3 +133,21 @@ def test_loss_restatement_matches_reference_loss_utils(golden_dir):
     assert abs(total.item() - float(g["loss"])) < 1e-6
     total.backward()
     np.testing.assert_allclose(a.grad.numpy(), g["grad"], rtol=1e-4, atol=1e-9)
+
+
+def test_points_pseudomesh_oracle_matches_reference(golden_dir):
+    """oracle/expansion.py points_* against PointsGaussianModel.prepare_vertices / prepare_scaling_rot / get_scaling
+    (games/flat_splatting/scene/points_gaussian_model.py:28-109)."""
+    g = _load(golden_dir, "points_model.npz")
+    tri = expansion.points_prepare_vertices(torch.tensor(g["pv_xyz"]), torch.tensor(g["pv_scaling"]),
+                                            torch.tensor(g["pv_rotation"]))
+    np.testing.assert_allclose(tri.numpy(), g["pv_triangles"], rtol=0, atol=1e-6)
+    sl, rot = expansion.points_prepare_scaling_rot(torch.tensor(g["triangles"]))
+    np.testing.assert_allclose(sl.numpy(), g["_scaling"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(rot.numpy(), g["_rotation"], atol=1e-6)
+    np.testing.assert_allclose(expansion.points_get_scaling(sl).numpy(), g["get_scaling"], rtol=1e-6, atol=1e-12)
+    # round trip: the triangle of a flat Gaussian maps back to the same in-plane scales (longer first) and the same frame
+    sl2, rot2 = expansion.points_prepare_scaling_rot(tri)
+    want = np.sort(g["pv_scaling"], axis=1)[:, ::-1]
+    np.testing.assert_allclose(sl2.numpy(), want, atol=2e-5)
+
