@@ -187,7 +187,10 @@ GMS_HD void gms_face_frame_backward(const float* t, float eps, const GmsFrame& f
 #define GMS_ATOMIC_ADD(p, v) (*(p) += (v))
 #endif
 
-GMS_HD void gms_expand_face_fwd(const gms_expand_args& a, int f) {
+// `f` indexes the per-FACE arrays (faces / triangles_in / triangles); `fl` indexes the per-GAUSSIAN streams (alpha_raw,
+// scale_raw and every output row): fl == f when they are the caller's arrays, fl == the face's slot in the block when the
+// kernel has redirected those pointers to its shared-memory staging buffers (k_expand_fwd / k_expand_bwd).
+GMS_HD void gms_expand_face_fwd(const gms_expand_args& a, int f, int fl) {
     float t[9];
     if (a.triangles_in) {
 #pragma unroll
@@ -210,7 +213,7 @@ GMS_HD void gms_expand_face_fwd(const gms_expand_args& a, int f) {
     gms_frame_quat(fr, q, ax);
     const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
     for (int k = 0; k < a.K; k++) {
-        const size_t p = (size_t)f * a.K + k;
+        const size_t p = (size_t)fl * a.K + k;
         const float r0 = fmaxf(a.alpha_raw[3 * p], 0.f) + 1e-8f, r1 = fmaxf(a.alpha_raw[3 * p + 1], 0.f) + 1e-8f,
                     r2 = fmaxf(a.alpha_raw[3 * p + 2], 0.f) + 1e-8f;
         const float S = r0 + r1 + r2;
@@ -232,7 +235,7 @@ GMS_HD void gms_expand_face_fwd(const gms_expand_args& a, int f) {
     }
 }
 
-GMS_HD void gms_expand_face_bwd(const gms_expand_args& a, const gms_expand_grads& g, int f) {
+GMS_HD void gms_expand_face_bwd(const gms_expand_args& a, const gms_expand_grads& g, int f, int fl) {
     float t[9];
     int64_t vi[3] = {0, 0, 0};
     if (a.triangles_in) {
@@ -258,7 +261,7 @@ GMS_HD void gms_expand_face_bwd(const gms_expand_args& a, const gms_expand_grads
     float dq[4] = {0.f, 0.f, 0.f, 0.f};
     float ds1 = 0.f, ds2 = 0.f;
     for (int k = 0; k < a.K; k++) {
-        const size_t p = (size_t)f * a.K + k;
+        const size_t p = (size_t)fl * a.K + k;
         // --- xyz = alpha @ triangle
         float dx[3] = {0.f, 0.f, 0.f};
         if (g.dL_dxyz) { dx[0] = g.dL_dxyz[3 * p]; dx[1] = g.dL_dxyz[3 * p + 1]; dx[2] = g.dL_dxyz[3 * p + 2]; }

@@ -56,23 +56,27 @@ class FlatAdam:
     def zero_grad(self):
         self.g.zero_()
 
-    def step(self):
+    def step(self, zero_end=None):
         """world == 1: one launch over the whole flat buffer (gradient zeroed in the same pass).
         world > 1: reduce-scatter(mean) -> Adam on the local slice -> all-gather of the parameters; the full gradient
-        buffer is re-zeroed with one memset."""
+        buffer is re-zeroed with one memset.
+        zero_end: when the producer of the gradients OVERWRITES everything at flat indices >= zero_end each frame
+        (gms_train_frame: all but the atomically accumulated vertex gradients), only [0, zero_end) is zeroed."""
         import torch.distributed as dist
         self.t += 1
         a = _lib.AdamArgs()
         if self.world > 1:
-            dist.reduce_scatter_tensor(self.g_shard, self.g, op=dist.ReduceOp.SUM)
-            self.g_shard.mul_(1.0 / self.world)
+            # NCCL averages inside the collective (exact for power-of-two world sizes): no separate scaling pass
+            dist.reduce_scatter_tensor(self.g_shard, self.g, op=dist.ReduceOp.AVG)
             off = self.rank * self.shard
             p_local = self.p[off:off + self.shard]
             a.n, a.offset = self.shard, off
             a.p, a.g, a.m, a.v = p_local.data_ptr(), self.g_shard.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
+            a.zero_grad = 0            # g_shard is overwritten by the next reduce-scatter
         else:
             a.n, a.offset = self.n, 0
             a.p, a.g, a.m, a.v = self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
+            a.zero_grad, a.zero_end = (1, 0) if zero_end is None else (2, int(zero_end))
         a.nseg = len(self.groups)
         for i, g in enumerate(self.groups):
             a.seg_end[i] = self.ends[i]
@@ -80,13 +84,16 @@ class FlatAdam:
             a.lr1[i] = float(g.get("lr1", g.get("lr", 0.0)))
             a.inner[i] = int(g.get("inner", 1))
             a.period[i] = int(g.get("period", 0))
-        a.beta1, a.beta2, a.eps, a.step, a.zero_grad = self.betas[0], self.betas[1], self.eps, self.t, 1
+        a.beta1, a.beta2, a.eps, a.step = self.betas[0], self.betas[1], self.eps, self.t
         dev = self.p.device
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gms_adam_step(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "gms_adam_step")
         if self.world > 1:
             dist.all_gather_into_tensor(self.p, p_local)
-            self.g.zero_()
+            (self.g if zero_end is None else self.g[:int(zero_end)]).zero_()
+
+    def zero_grad_partial(self, zero_end=None):
+        (self.g if zero_end is None else self.g[:int(zero_end)]).zero_()
 
 
 def mesh_model_groups(model, lrs=REFERENCE_LRS) -> List[dict]:

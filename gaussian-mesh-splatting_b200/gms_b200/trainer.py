@@ -158,10 +158,11 @@ class MeshTrainer:
                 if loss_ready is not None:
                     loss_ready.record(torch.cuda.current_stream(loss.device))
             self._all_reduce()
+            # gms_train_frame overwrites every gradient except the atomically accumulated vertex segment (group 0)
             if self.optimizer_step:
-                self.opt.step()
+                self.opt.step(zero_end=self.opt.ends[0])
             else:
-                self.opt.zero_grad()
+                self.opt.zero_grad_partial(self.opt.ends[0])
             return loss
         from . import rasterizer as _r
         prev = _r.DIRECT_SH_GRAD

@@ -243,7 +243,7 @@ int gms_loss_scratch_bytes(int32_t C, int32_t H, int32_t W, size_t* bytes);
 int gms_l1_ssim_loss(const gms_loss_args* a, void* cuda_stream);
 
 /* torch.optim.Adam(groups, eps=1e-15) of gaussian_mesh_model.py:171-183 (train.py:146-148) over ONE flat fp32
- * parameter buffer, one launch; consumes and (optionally) zeroes the gradient in the same pass.
+ * parameter buffer, one launch; consumes and (optionally, fully or only a leading range) zeroes the gradient in the same pass.
  * Segment i covers flat indices [seg_end[i-1], seg_end[i]); lr = lr0[i], or -- when period[i] > 0 --
  * lr0[i] where ((index - segment start) / inner[i]) % period[i] == 0 and lr1[i] elsewhere (DC vs rest SH). */
 typedef struct gms_adam_args {
@@ -256,7 +256,9 @@ typedef struct gms_adam_args {
     int32_t inner[8]; int32_t period[8];
     float beta1, beta2, eps;
     int32_t step;            /* 1-based step count (bias correction) */
-    int32_t zero_grad;
+    int32_t zero_grad;       /* 0: leave g; 1: zero every consumed element; 2: zero only flat indices < zero_end */
+    int64_t zero_end;        /* (mode 2) e.g. the end of the vertices segment when every other gradient is overwritten
+                                by the next frame (gms_train_frame) */
 } gms_adam_args;
 int gms_adam_step(const gms_adam_args* a, void* cuda_stream);
 
@@ -295,8 +297,9 @@ int64_t gms_launch_count(int reset);
  * while option "time_kernels" is 1.  Fills up to max_kernels entries (accumulated ms, launch count, name) and
  * returns the number of kernel slots. */
 int gms_kernel_times(int reset, int max_kernels, double* ms_out, int64_t* count_out, const char** names_out);
-/* Tuning knobs (round-over-round experiments): "quad_masks", "warp_emit", "time_kernels".
- * Returns the previous value; unknown keys return -1. */
+/* Tuning knobs (round-over-round experiments): "quad_masks", "warp_emit", "time_kernels", "composite_version",
+ * "composite_fwd", "composite_bwd", "bwd_minblocks", "tile_order", "sort_impl", "expand_staged", "sh_staged"
+ * (DESIGN.md lists what each selects).  Returns the previous value; unknown keys return -1. */
 int gms_set_option(const char* key, int value);
 
 #ifdef __cplusplus

@@ -10,12 +10,12 @@
 extern "C" {
 
 int shim_expand_forward(const gms_expand_args* a) {
-    for (int f = 0; f < a->F; f++) gms_expand_face_fwd(*a, f);
+    for (int f = 0; f < a->F; f++) gms_expand_face_fwd(*a, f, f);
     return 0;
 }
 
 int shim_expand_backward(const gms_expand_args* a, const gms_expand_grads* g) {
-    for (int f = 0; f < a->F; f++) gms_expand_face_bwd(*a, *g, f);
+    for (int f = 0; f < a->F; f++) gms_expand_face_bwd(*a, *g, f, f);
     return 0;
 }
 

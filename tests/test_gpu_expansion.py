@@ -194,3 +194,38 @@ def test_points_prepare_vertices_matches_golden_and_oracle(golden_dir):
     longer_first = torch.sort(sl[:, 1:], dim=1, descending=True).values
     np.testing.assert_allclose(m._scaling.cpu().numpy(), longer_first.numpy(), atol=1e-4)
 
+
+@pytest.mark.parametrize("level,K", [(2, 1), (3, 3), (3, 7), (1, 40)])
+def test_staged_and_direct_expansion_kernels_agree(level, K):
+    """Option "expand_staged": per-Gaussian streams through shared memory (default) vs direct global accesses -- the same
+    per-face arithmetic, so every output and gradient but the atomically accumulated vertex gradient is bit-identical.
+    F is not a multiple of the 128-face block; K = 40 exceeds the 48 KB staging limit (falls back to the direct kernel)."""
+    from gms_b200 import _lib
+    p = scenes.init_mesh_gaussians(*scenes.icosphere(level), K=K, seed=4)
+    gen = torch.Generator().manual_seed(1)
+    res = []
+    try:
+        for staged in (1, 0):
+            _lib.set_option("expand_staged", staged)
+            m = MeshGaussianModel.from_params(p, "cuda")
+            P = m._scale.shape[0]
+            if not res:
+                w = [torch.randn(P, c, generator=gen).cuda() for c in (3, 3, 4)]
+            outs = []
+            for activated in (False, True):
+                xyz, sc, rot = m.expand_fused(activated=activated)
+                ((xyz * w[0]).sum() + (sc * w[1]).sum() + (rot * w[2]).sum()).backward()
+                outs += [xyz.detach(), sc.detach(), rot.detach()]
+            res.append((outs, [m.vertices.grad.clone(), m._alpha.grad.clone(), m._scale.grad.clone()]))
+    finally:
+        _lib.set_option("expand_staged", 1)
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[0][1][1], res[1][1][1]) and torch.equal(res[0][1][2], res[1][1][2])
+    np.testing.assert_allclose(res[0][1][0].cpu().numpy(), res[1][1][0].cpu().numpy(), rtol=1e-4, atol=1e-5)
+    # and against the oracle (reference-pinned restatement)
+    oxyz, osl, orr, _, _ = oexp.expand(p.vertices, p.faces, p._alpha, p._scale)
+    np.testing.assert_allclose(res[0][0][0].cpu().numpy(), oxyz.numpy(), atol=1e-6)
+    np.testing.assert_allclose(res[0][0][1].cpu().numpy(), osl.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(res[0][0][2].cpu().numpy(), orr.numpy(), atol=2e-6)
+

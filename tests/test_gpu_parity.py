@@ -150,6 +150,30 @@ def test_sort_implementations_give_the_stock_order(impl, P, W, H):
     assert_forward_parity(st, color, radii, invd, state)
 
 
+@pytest.mark.parametrize("P,deg", [(4001, 3), (77, 1), (12345, 0)])
+def test_sh_tile_staging_is_bit_identical_to_direct_access(P, deg):
+    """Option "sh_staged": SH rows (and their gradient rows) through the per-warp shared-memory tile vs per-lane global
+    accesses.  Same arithmetic: colours, radii and dL/dshs (written, not accumulated) must be bit-identical, including the
+    zero rows of culled Gaussians and a last warp that is only partly inside P."""
+    S, g = _case(P, 200, 152, seed=P, sh_degree=deg, extent=2.5)      # extent 2.5: a good share of the splats is culled
+    dC, dI = _grads_in(152, 200, 9)
+    res = []
+    try:
+        for staged in (1, 0):
+            _lib.set_option("sh_staged", staged)
+            res.append(run_gpu(S, g, dC, dI))
+    finally:
+        _lib.set_option("sh_staged", 1)
+    a, b = res
+    np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[4]["shs"], b[4]["shs"])
+    assert (a[1] == 0).any() and (a[1] > 0).any()
+    assert np.abs(a[4]["shs"][a[1] == 0]).max() == 0.0
+    st, gref = run_oracle(S, g, dC, dI)
+    assert_forward_parity(st, a[0], a[1], a[2], a[3])
+    assert_grad_parity(a[4], gref)
+
+
 def test_empty_and_invisible_inputs():
     S, g = _case(10, 64, 64, seed=1)
     e = {k: v[:0] for k, v in g.items()}

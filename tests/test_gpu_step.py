@@ -63,6 +63,50 @@ def test_flat_adam_matches_torch_adam():
                                torch.cat((m2._features_dc, m2._features_rest), 1).detach().cpu().numpy(), rtol=2e-5, atol=2e-7)
 
 
+def test_adam_abi_unaligned_segments_offsets_and_partial_zero():
+    """gms_adam_step through the raw C ABI: segment ends that are NOT multiples of 4 (per-element path), a shard offset, the
+    DC/rest learning-rate phase of a packed segment, and zero_grad mode 2 (only flat indices < zero_end are cleared);
+    against a float64 restatement of torch.optim.Adam's update (gaussian_mesh_model.py:183)."""
+    import ctypes as C
+    from gms_b200 import _lib
+    gen = torch.Generator().manual_seed(5)
+    n_total = 64 * 37
+    ends = [101, 101 + 48 * 19 + 2, n_total]            # packed segment in the middle: inner 3, period 16
+    lr0, lr1, inner, period = [1e-2, 3e-3, 5e-2], [1e-2, 2e-4, 5e-2], [1, 3, 1], [0, 16, 0]
+    p0 = torch.randn(n_total, generator=gen); g0 = torch.randn(n_total, generator=gen) * 0.1
+    m0 = torch.randn(n_total, generator=gen) * 0.01; v0 = torch.rand(n_total, generator=gen) * 1e-3
+    idx = torch.arange(n_total)
+    lr = torch.full((n_total,), lr0[2], dtype=torch.float64)
+    lr[idx < ends[1]] = torch.where(((idx[idx < ends[1]] - ends[0]) // 3) % 16 == 0, lr0[1], lr1[1]).double()
+    lr[idx < ends[0]] = lr0[0]
+    step, b1, b2, eps = 7, 0.9, 0.999, 1e-15
+    m_ref = b1 * m0.double() + (1 - b1) * g0.double()
+    v_ref = b2 * v0.double() + (1 - b2) * g0.double() ** 2
+    p_ref = p0.double() - lr / (1 - b1 ** step) * m_ref / (v_ref.sqrt() / (1 - b2 ** step) ** 0.5 + eps)
+    for off, n, zero_mode, zero_end in ((0, n_total, 2, 150), (64 * 5, 64 * 20, 1, 0), (4, n_total - 4 - 3, 0, 0)):
+        p, g, m, v = (t.clone().cuda() for t in (p0, g0, m0, v0))
+        a = _lib.AdamArgs()
+        a.n, a.offset = n, off
+        a.p, a.g, a.m, a.v = (t[off:].data_ptr() for t in (p, g, m, v))
+        a.nseg = 3
+        for i in range(3):
+            a.seg_end[i], a.lr0[i], a.lr1[i], a.inner[i], a.period[i] = ends[i], lr0[i], lr1[i], inner[i], period[i]
+        a.beta1, a.beta2, a.eps, a.step, a.zero_grad, a.zero_end = b1, b2, eps, step, zero_mode, zero_end
+        _lib.check(_lib.lib().gms_adam_step(C.byref(a), torch.cuda.current_stream().cuda_stream), "gms_adam_step")
+        sl = slice(off, off + n)
+        np.testing.assert_allclose(p.cpu()[sl].numpy(), p_ref[sl].float().numpy(), rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(m.cpu()[sl].numpy(), m_ref[sl].float().numpy(), rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(v.cpu()[sl].numpy(), v_ref[sl].float().numpy(), rtol=2e-6, atol=1e-12)
+        untouched = torch.ones(n_total, dtype=torch.bool); untouched[sl] = False
+        assert torch.equal(p.cpu()[untouched], p0[untouched]) and torch.equal(g.cpu()[untouched], g0[untouched])
+        want_g = g0.clone()
+        if zero_mode == 1:
+            want_g[sl] = 0
+        elif zero_mode == 2:
+            want_g[off:min(off + n, zero_end)] = 0
+        assert torch.equal(g.cpu(), want_g)
+
+
 def test_fast_trainer_equals_reference_ordered_step():
     """One optimisation step: fused expansion + packed SH + fused loss + FlatAdam  ==  two-step expansion + getters +
     ATen loss + torch.optim.Adam (the reference's op sequence, train.py:89-157) on the same rasterizer."""
