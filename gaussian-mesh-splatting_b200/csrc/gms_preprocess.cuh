@@ -322,7 +322,7 @@ GMS_HD void gms_preprocess_backward_geom(const float* mean, const float* scale, 
 }
 
 // Appendix A.4 (iii): SH backward.  Writes dsh[3*k+ch] for k < (deg+1)^2 (rest zero) and ADDS the view-direction
-// term to dmean.  dcolor is the (unmasked) colour gradient; clamped masks it.
+// term to dmean.  `dsh` may alias `sh` (k_preprocess_bwd's in-place shared-memory row).  dcolor is the (unmasked) colour gradient; clamped masks it.
 GMS_HD void gms_sh_backward(int deg, int M, const float* mean, const float* campos, const float* sh,
                             const float* dcolor, const uint8_t* clamped, float* dsh, float* dmean) {
     const float vx = mean[0] - campos[0], vy = mean[1] - campos[1], vz = mean[2] - campos[2];
@@ -334,6 +334,10 @@ GMS_HD void gms_sh_backward(int deg, int M, const float* mean, const float* camp
     float B[16];
     gms_sh_basis(deg, x, y, z, B);
     const int nc = (deg + 1) * (deg + 1);
+    // t_k = sum_ch sh[k][ch] * g[ch]   (every read of sh[] precedes the writes of dsh[]: the two may be the same row)
+    float t[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) t[k] = (k < nc) ? (sh[3 * k] * g[0] + sh[3 * k + 1] * g[1] + sh[3 * k + 2] * g[2]) : 0.f;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         if (k < M) {
@@ -341,10 +345,6 @@ GMS_HD void gms_sh_backward(int deg, int M, const float* mean, const float* camp
             dsh[3 * k + 0] = bk * g[0]; dsh[3 * k + 1] = bk * g[1]; dsh[3 * k + 2] = bk * g[2];
         }
     }
-    // t_k = sum_ch sh[k][ch] * g[ch]
-    float t[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) t[k] = (k < nc) ? (sh[3 * k] * g[0] + sh[3 * k + 1] * g[1] + sh[3 * k + 2] * g[2]) : 0.f;
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;
     if (deg > 0) {
         ddy += -GMS_SH_C1 * t[1]; ddz += GMS_SH_C1 * t[2]; ddx += -GMS_SH_C1 * t[3];

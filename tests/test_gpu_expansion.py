@@ -204,8 +204,9 @@ def test_staged_and_direct_expansion_kernels_agree(level, K):
     p = scenes.init_mesh_gaussians(*scenes.icosphere(level), K=K, seed=4)
     gen = torch.Generator().manual_seed(1)
     res = []
+    default = _lib.set_option("expand_staged", 3)
     try:
-        for staged in (1, 0):
+        for staged in (3, 0):         # bit 0: forward staged, bit 1: backward staged
             _lib.set_option("expand_staged", staged)
             m = MeshGaussianModel.from_params(p, "cuda")
             P = m._scale.shape[0]
@@ -218,7 +219,7 @@ def test_staged_and_direct_expansion_kernels_agree(level, K):
                 outs += [xyz.detach(), sc.detach(), rot.detach()]
             res.append((outs, [m.vertices.grad.clone(), m._alpha.grad.clone(), m._scale.grad.clone()]))
     finally:
-        _lib.set_option("expand_staged", 1)
+        _lib.set_option("expand_staged", default)
     for a, b in zip(res[0][0], res[1][0]):
         assert torch.equal(a, b)
     assert torch.equal(res[0][1][1], res[1][1][1]) and torch.equal(res[0][1][2], res[1][1][2])

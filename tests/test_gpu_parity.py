@@ -158,15 +158,18 @@ def test_sh_tile_staging_is_bit_identical_to_direct_access(P, deg):
     S, g = _case(P, 200, 152, seed=P, sh_degree=deg, extent=2.5)      # extent 2.5: a good share of the splats is culled
     dC, dI = _grads_in(152, 200, 9)
     res = []
+    default = _lib.set_option("sh_staged", 2)
     try:
-        for staged in (1, 0):
+        for staged in (2, 1, 0):      # 2: gradient rows computed in place in the tile; 1: register copies; 0: direct
             _lib.set_option("sh_staged", staged)
             res.append(run_gpu(S, g, dC, dI))
     finally:
-        _lib.set_option("sh_staged", 1)
-    a, b = res
-    np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
-    np.testing.assert_array_equal(a[4]["shs"], b[4]["shs"])
+        _lib.set_option("sh_staged", default)
+    a = res[0]
+    for b in res[1:]:
+        np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
+        np.testing.assert_array_equal(a[4]["shs"], b[4]["shs"])
+        np.testing.assert_array_equal(a[4]["opacities"], b[4]["opacities"])
     assert (a[1] == 0).any() and (a[1] > 0).any()
     assert np.abs(a[4]["shs"][a[1] == 0]).max() == 0.0
     st, gref = run_oracle(S, g, dC, dI)

@@ -95,7 +95,7 @@ def test_adam_abi_unaligned_segments_offsets_and_partial_zero():
         _lib.check(_lib.lib().gms_adam_step(C.byref(a), torch.cuda.current_stream().cuda_stream), "gms_adam_step")
         sl = slice(off, off + n)
         np.testing.assert_allclose(p.cpu()[sl].numpy(), p_ref[sl].float().numpy(), rtol=2e-5, atol=1e-7)
-        np.testing.assert_allclose(m.cpu()[sl].numpy(), m_ref[sl].float().numpy(), rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(m.cpu()[sl].numpy(), m_ref[sl].float().numpy(), rtol=2e-6, atol=2e-8)   # fp32 ulp of 0.9*m + 0.1*g
         np.testing.assert_allclose(v.cpu()[sl].numpy(), v_ref[sl].float().numpy(), rtol=2e-6, atol=1e-12)
         untouched = torch.ones(n_total, dtype=torch.bool); untouched[sl] = False
         assert torch.equal(p.cpu()[untouched], p0[untouched]) and torch.equal(g.cpu()[untouched], g0[untouched])
