@@ -93,9 +93,9 @@ class LossArgs(C.Structure):
 
 class AdamArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("offset", C.c_int64), ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
-                ("nseg", C.c_int32), ("seg_end", C.c_int64 * 8), ("lr0", C.c_float * 8), ("lr1", C.c_float * 8),
-                ("inner", C.c_int32 * 8), ("period", C.c_int32 * 8), ("beta1", C.c_float), ("beta2", C.c_float),
-                ("eps", C.c_float), ("step", C.c_int32), ("zero_grad", C.c_int32), ("zero_end", C.c_int64)]
+                ("nseg", C.c_int32), ("seg_end", C.c_int64 * 8), ("lr0", C.c_double * 8), ("lr1", C.c_double * 8),
+                ("inner", C.c_int32 * 8), ("period", C.c_int32 * 8), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("step", C.c_int32), ("zero_grad", C.c_int32), ("zero_end", C.c_int64)]
 
 
 class FrameArgs(C.Structure):

@@ -252,9 +252,9 @@ typedef struct gms_adam_args {
     float* p; float* g; float* m; float* v;   /* pointers to element `offset` of the respective flat buffers */
     int32_t nseg;
     int64_t seg_end[8];
-    float lr0[8]; float lr1[8];
+    double lr0[8]; double lr1[8];   /* doubles, like torch's Python-float hyper-parameters: lr / (1 - beta1^t), 1 - beta */
     int32_t inner[8]; int32_t period[8];
-    float beta1, beta2, eps;
+    double beta1, beta2, eps;       /* and sqrt(1 - beta2^t) are formed in double and rounded to fp32 once */
     int32_t step;            /* 1-based step count (bias correction) */
     int32_t zero_grad;       /* 0: leave g; 1: zero every consumed element; 2: zero only flat indices < zero_end */
     int64_t zero_end;        /* (mode 2) e.g. the end of the vertices segment when every other gradient is overwritten
