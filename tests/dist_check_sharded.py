@@ -29,12 +29,16 @@ def main():
     gt_model = MeshGaussianModel.from_params(scenes.init_mesh_gaussians(*scenes.icosphere(4), K=3, seed=77), dev)
     with torch.no_grad():
         gts = [render_frame(gt_model, c, bg)[0].clamp(0, 1).contiguous() for c in cams]
-    # distributed run
-    m = MeshGaussianModel.from_params(p, dev, packed_features=True)
-    tr = MeshTrainer(m, bg, world=world, rank=rank, fast=True)
-    for s in range(3):
-        ci = shard_cameras(len(cams), s, rank, world)
-        tr.step(cams[ci], gts[ci])
+    # distributed runs: autograd fast path (full gradient re-zeroing) and the one-call native frame (only the vertex
+    # segment is re-zeroed, every other gradient is overwritten by the next frame)
+    runs = {}
+    for native in (False, True):
+        m = MeshGaussianModel.from_params(p, dev, packed_features=True)
+        tr = MeshTrainer(m, bg, world=world, rank=rank, fast=True, native=native)
+        for s in range(3):
+            ci = shard_cameras(len(cams), s, rank, world)
+            tr.step(cams[ci], gts[ci])
+        runs[native] = (m, tr)
     # single-process reference on every rank: average the per-camera gradients by hand
     r = MeshGaussianModel.from_params(p, dev, packed_features=True)
     rt = MeshTrainer(r, bg, world=1, rank=0, fast=True)
@@ -46,15 +50,16 @@ def main():
             image, _, _ = render_frame(r, cams[ci], bg)
             (fused_training_loss(image, gts[ci], 0.2) / world).backward()
         rt.opt.step()
-    worst = 0.0
-    for a, b in zip(m.parameters(), r.parameters()):
-        scale = b.detach().abs().max().item() + 1e-12
-        worst = max(worst, (a.detach() - b.detach()).abs().max().item() / scale)
-    # replicas agree bit for bit across ranks (all-gather of the same slices)
-    flat = tr.opt.p.clone()
-    other = flat.clone()
-    dist.broadcast(other, src=0)
-    same = bool(torch.equal(flat, other))
+    worst, same = 0.0, True
+    for native, (m, tr) in runs.items():
+        for a, b in zip(m.parameters(), r.parameters()):
+            scale = b.detach().abs().max().item() + 1e-12
+            worst = max(worst, (a.detach() - b.detach()).abs().max().item() / scale)
+        # replicas agree bit for bit across ranks (all-gather of the same slices)
+        flat = tr.opt.p.clone()
+        other = flat.clone()
+        dist.broadcast(other, src=0)
+        same = same and bool(torch.equal(flat, other))
     t = torch.tensor([worst, 0.0 if same else 1.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
