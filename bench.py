@@ -23,8 +23,17 @@ for p in (ROOT, os.path.join(ROOT, "gaussian-mesh-splatting_b200"), os.path.join
     if p not in sys.path:
         sys.path.insert(0, p)
 
-# NCCL writes its version banner to stdout; the driver expects ONE JSON line there
+# The driver expects ONE JSON line on stdout.  NCCL prints its version banner with printf to fd 1 (NCCL_DEBUG_FILE does
+# not cover it): keep the real stdout aside for the result line and point fd 1 at stderr for everything else.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_result(line: dict) -> None:
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -193,7 +202,7 @@ def run_reference_arm(args):
             "gpu_launches": 0,
             "note": "reference arm = CPU oracle port of the reference algorithm (stock diff-gaussian-rasterization source is "
                     "absent from the reference checkout: empty submodule)"}
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 # ----------------------------------------------------------------------------------------------- animated render
@@ -241,12 +250,12 @@ def run_render_animated(args, params, cams, dims, dev, world, rank, local):
     launches = _lib.launch_count(reset=True)
     if rank == 0:
         ms_step = float(ms.item()) / K_
-        print(json.dumps({"metric": "frames/sec (forward only, animated-vertex sweep) @1080p", "value": world * 1000.0 / ms_step,
+        emit_result({"metric": "frames/sec (forward only, animated-vertex sweep) @1080p", "value": world * 1000.0 / ms_step,
                           "unit": "frames/s", "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": ms_step,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": args.workload, "mode": "render_animated", "P": F * K, "faces": F, "K": K, "width": W,
                                      "height": H, "sh_degree": 3, "n_frames": n_frames, "N_last": rasterizer.last_num_rendered},
-                          "gpu_launches": int(launches)}), flush=True)
+                          "gpu_launches": int(launches)})
     if world > 1:
         dist.destroy_process_group()
 
@@ -468,7 +477,7 @@ def main():
             line["cpu_baseline"] = {"value": 1.0 / fs, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-    print(json.dumps(line), flush=True)
+    emit_result(line)
     if world > 1:
         dist.destroy_process_group()
 
