@@ -56,9 +56,9 @@ ALGO_BYTES = {  # algorithmic bytes per unit, SURVEY.md section 8(d) / DESIGN.md
 
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
-# this workload (profiles/r1i_composite_bwd3_ncu_summary.csv, profiles/r1i_composite_ncu_summary.csv); ncu replays the
-# kernel, so these are constants here, not measured inside the timed run.
-NCU_TRAFFIC_BYTES = {("gs_mesh_1M_1080p", "composite_bwd"): 131.51e6 + 17.29e6, ("gs_mesh_1M_1080p", "composite_fwd"): 53.69e6 + 11.74e6}
+# this workload (profiles/r1v_ncu_full_bwd3_prebwd_adam_summary.csv, profiles/r1i_composite_ncu_summary.csv); ncu replays
+# the kernel, so these are constants here, not measured inside the timed run.
+NCU_TRAFFIC_BYTES = {("gs_mesh_1M_1080p", "composite_bwd"): 133.85e6 + 20.61e6, ("gs_mesh_1M_1080p", "composite_fwd"): 53.69e6 + 11.74e6}
 
 
 def build_scene(name, seed=0):
