@@ -253,6 +253,23 @@ __device__ __forceinline__ void gms_fold10(const float (&v)[10], int lane, float
     out = z;
 }
 
+// Loop-hoisted form of gms_fold10 for the streaming kernels: the (lane-constant) destination slot is computed once
+// before the splat loop -- gms_fold_slot(): idx of the sum this lane ends up with, or -1 -- and made opaque so that the
+// compiler keeps it in a register instead of re-deriving it from %tid.x in every iteration (9 instructions + S2R).
+__device__ __forceinline__ int gms_fold_slot(int lane) {
+    const int i1 = (lane & 8) ? 3 : 0, i2 = (lane & 4) ? 2 : 0, i3 = (lane & 2) ? 1 : 0;
+    const int xi = i2 + i3;
+    const bool valid = (xi <= 2) && (i1 + xi <= 4) && ((lane & 1) == 0);
+    int slot = valid ? ((lane & 16) ? 5 : 0) + i1 + xi : -1;
+    asm volatile("" : "+r"(slot));
+    return slot;
+}
+__device__ __forceinline__ float gms_fold10_sum(const float (&v)[10], int lane) {
+    float out; int idx; bool valid;
+    gms_fold10(v, lane, out, idx, valid);      // idx / valid are dead here and drop out
+    return out;
+}
+
 struct GmsBwdPix {
     float T, Tfin, accum[3], lastc[3], accum_inv, last_inv, last_alpha, dpix[3], dinv, bg_dot;
     int last;

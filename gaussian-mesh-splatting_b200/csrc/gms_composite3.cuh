@@ -203,6 +203,7 @@ k_composite_bwd3(const int2* __restrict__ ranges, const int* __restrict__ tile_o
     const size_t HW = (size_t)H * W;
     const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
     GmsSlab3B& S = s_slab[warp];
+    const int slot = gms_fold_slot(lane);      // where this lane's share of the warp sums goes (-1: none)
 
     // per-pixel-pair state
     f2 T, nTfin, dpr, dpg, dpb, dpd, bgdot;
@@ -295,9 +296,8 @@ k_composite_bwd3(const int2* __restrict__ ranges, const int* __restrict__ tile_o
             float v[10];
             v[0] = qx.x + qx.y; v[1] = qy.x + qy.y; v[2] = pxx.x + pxx.y; v[3] = pxy.x + pxy.y; v[4] = pyy.x + pyy.y;
             v[5] = q.x + q.y; v[6] = wr.x + wr.y; v[7] = wg.x + wg.y; v[8] = wb.x + wb.y; v[9] = wd.x + wd.y;
-            float out; int idx; bool valid;
-            gms_fold10(v, lane, out, idx, valid);
-            if (valid) S.part[j][idx] = out;
+            const float out = gms_fold10_sum(v, lane);
+            if (slot >= 0) S.part[j][slot] = out;
             touched |= 1u << j;
         }
         __syncwarp();
