@@ -184,15 +184,37 @@ struct GmsSlab3B {
     float part[GMS_WB][12];
 };
 
+// Deferred warp reduction (RED = 1): instead of the 12-shuffle transpose-fold per blended splat, every lane parks its NV
+// partial sums of up to three splats in a [3*NV][32] shared-memory panel (row stride 36 floats: conflict-free column
+// stores and conflict-free 128-bit row loads); lane r then adds up row r (8 LDS.128 + 31 FADD for three splats at once)
+// and writes S.part.  Same sums, different association order.
+constexpr int GMS_RED_STRIDE = 36, GMS_RED_ROWS = 30;
+
+template <int NV>
+__device__ __forceinline__ void gms_red_flush(const float* red, float (*part)[12], int pj, int nrows, int lane, int rk8, int ri) {
+    __syncwarp();
+    if (lane < nrows) {
+        const float4* row = reinterpret_cast<const float4*>(red + lane * GMS_RED_STRIDE);
+        const float4 a = row[0];
+        float s0 = a.x + a.y, s1 = a.z + a.w;
+#pragma unroll
+        for (int c = 1; c < 8; c++) { const float4 t = row[c]; s0 += t.x; s1 += t.z; s0 += t.y; s1 += t.w; }
+        part[(pj >> rk8) & 31][ri] = s0 + s1;
+    }
+    __syncwarp();
+}
+
 // DEPTH = false: no loss on the inverse-depth image (train.py never puts one): the depth channel of the recurrence and its
 // moment sum are compiled out.
-template <int MINB, bool DEPTH>
+template <int MINB, bool DEPTH, int RED = 0>
 __global__ void __launch_bounds__(GMS_CB, MINB)
 k_composite_bwd3(const int2* __restrict__ ranges, const int* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
                  const float4* __restrict__ recs, int W, int H, int gx, const float* __restrict__ bg,
                  const float* __restrict__ final_T, const int* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpix, const float* __restrict__ dL_dinv, float4* __restrict__ dgeom) {
     __shared__ GmsSlab3B s_slab[4];
+    __shared__ __align__(16) float s_red[RED ? 4 : 1][RED ? GMS_RED_ROWS * GMS_RED_STRIDE : 4];
+    constexpr int NV = DEPTH ? 10 : 9;         // partial sums per splat (RED path; the fold always carries 10)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;
     const GmsTileGeom g = gms_tile_geom(tile, gx, W, H, warp, lane);
@@ -203,7 +225,11 @@ k_composite_bwd3(const int2* __restrict__ ranges, const int* __restrict__ tile_o
     const size_t HW = (size_t)H * W;
     const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
     GmsSlab3B& S = s_slab[warp];
-    const int slot = gms_fold_slot(lane);      // where this lane's share of the warp sums goes (-1: none)
+    const int slot = RED ? -1 : gms_fold_slot(lane);      // where this lane's share of the warp sums goes (-1: none)
+    float* red = s_red[RED ? warp : 0];
+    int rk8 = 8 * (lane / NV), ri = lane % NV;            // RED: lane r sums panel row r = (pending splat r / NV, value r % NV)
+    asm volatile("" : "+r"(rk8), "+r"(ri));
+    int pend = 0, pj = 0;                                 // RED: pending splats in the panel, their slab indices (8 bits each)
 
     // per-pixel-pair state
     f2 T, nTfin, dpr, dpg, dpb, dpd, bgdot;
@@ -296,16 +322,26 @@ k_composite_bwd3(const int2* __restrict__ ranges, const int* __restrict__ tile_o
             float v[10];
             v[0] = qx.x + qx.y; v[1] = qy.x + qy.y; v[2] = pxx.x + pxx.y; v[3] = pxy.x + pxy.y; v[4] = pyy.x + pyy.y;
             v[5] = q.x + q.y; v[6] = wr.x + wr.y; v[7] = wg.x + wg.y; v[8] = wb.x + wb.y; v[9] = wd.x + wd.y;
-            const float out = gms_fold10_sum(v, lane);
-            if (slot >= 0) S.part[j][slot] = out;
+            if (RED) {
+                float* col = red + (pend * NV) * GMS_RED_STRIDE + lane;
+#pragma unroll
+                for (int i = 0; i < NV; i++) col[i * GMS_RED_STRIDE] = v[i];
+                pj |= j << (8 * pend);
+                if (++pend == 3) { gms_red_flush<NV>(red, S.part, pj, 3 * NV, lane, rk8, ri); pend = 0; pj = 0; }
+            } else {
+                const float out = gms_fold10_sum(v, lane);
+                if (slot >= 0) S.part[j][slot] = out;
+            }
             touched |= 1u << j;
         }
+        if (RED && pend) { gms_red_flush<NV>(red, S.part, pj, pend * NV, lane, rk8, ri); pend = 0; pj = 0; }
         __syncwarp();
         if ((touched >> lane) & 1u) {
             const int id = S.id[lane];
             const float4 s0 = *reinterpret_cast<const float4*>(&S.part[lane][0]);
             const float4 s1 = *reinterpret_cast<const float4*>(&S.part[lane][4]);
-            const float2 s2 = *reinterpret_cast<const float2*>(&S.part[lane][8]);
+            float2 s2 = *reinterpret_cast<const float2*>(&S.part[lane][8]);
+            if (RED && !DEPTH) s2.y = 0.f;         // the 9-value panel never writes the inverse-depth sum
             const float4 Q1 = S.q1[lane], Q2 = S.q2[lane];
             const float conx = Q1.x, ncony = Q1.z, conz = Q2.x, op = Q2.z;
             float4 g0, g1;

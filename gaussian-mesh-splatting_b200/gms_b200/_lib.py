@@ -162,6 +162,11 @@ def lib():
     L.gms_frame_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.gms_train_frame.argtypes = [C.POINTER(FrameArgs), ALLOC_FN, C.c_void_p, C.c_void_p]
     _lib = L
+    # GMS_OPTIONS="key=value,key=value": tuning knobs applied at load (A/B runs of whole test suites / benches)
+    for kv in filter(None, os.environ.get("GMS_OPTIONS", "").split(",")):
+        k, _, v = kv.partition("=")
+        if L.gms_set_option(k.strip().encode(), int(v)) == -1:
+            raise GmsLibraryError(f"GMS_OPTIONS: unknown option {k!r}")
     return L
 
 
