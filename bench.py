@@ -143,7 +143,11 @@ def cpu_reference_frame(params, cam, dims, budget_s, threads=None):
     from oracle import raster
     from helpers import settings_from_camera
     F, K, W, H = dims
-    cores = raster.num_threads() if threads is None else threads
+    if threads is None:     # every host core this process may use -- torchrun exports OMP_NUM_THREADS=1 by default
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    raster.set_num_threads(threads)
+    torch.set_num_threads(threads)
+    cores = raster.num_threads()
     S = settings_from_camera(cam, bg=(1, 1, 1))
     t0 = time.perf_counter()
     tv, ta, ts = (x.clone().requires_grad_(True) for x in (params.vertices, params._alpha, params._scale))

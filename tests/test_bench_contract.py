@@ -31,3 +31,21 @@ def test_ours_arm_fails_loudly_without_a_gpu():
                         "--no-cpu-baseline"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0
     assert not [l for l in r.stdout.split("\n") if l.strip().startswith("{")]
+
+
+def test_reference_arm_under_torchrun_prints_once_and_uses_the_host_cores():
+    """N > 1 launch of the reference arm (the driver uses torchrun for every N > 1): rank 0 alone measures and prints,
+    the other rank exits 0 without output; torchrun's OMP_NUM_THREADS=1 default must not throttle the CPU arm."""
+    env = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--workload", "tiny", "--steps", "1", "--warmup", "0",
+                        "--cpu-budget", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.split("\n") if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    assert d["cpu_baseline"]["cores"] == ncpu
+
