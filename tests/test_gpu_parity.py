@@ -135,15 +135,16 @@ def test_composite_generations_agree_and_match_oracle(version, tile_order):
     assert_grad_parity(grads, gref)
 
 
+@pytest.mark.parametrize("reduce", [1, 0])
 @pytest.mark.parametrize("with_depth", [True, False])
 @pytest.mark.parametrize("P,W,H", [(20000, 400, 300), (3000, 333, 201)])
-def test_backward_deferred_shared_memory_reduction(P, W, H, with_depth):
-    """Option "bwd_reduce" = 1: k_composite_bwd3 parks the per-lane moment sums of up to three splats in a shared-memory
-    panel and reduces rows instead of shuffle-folding every splat; both template variants (with / without the
-    inverse-depth channel), full and partial panels, ragged image."""
+def test_backward_warp_reduction_variants(P, W, H, with_depth, reduce):
+    """Option "bwd_reduce": 1 (default) -- k_composite_bwd3 parks the per-lane moment sums of up to three splats in a
+    shared-memory panel and reduces rows; 0 -- 12-shuffle transpose-fold per splat.  Both template variants (with /
+    without the inverse-depth channel), full and partial panels, ragged image."""
     S, g = _case(P, W, H, seed=P + 1)
     dC, dI = _grads_in(H, W, 5)
-    old = _lib.set_option("bwd_reduce", 1)
+    old = _lib.set_option("bwd_reduce", reduce)
     try:
         color, radii, invd, state, grads = run_gpu(S, g, dC, dI if with_depth else None)
     finally:
