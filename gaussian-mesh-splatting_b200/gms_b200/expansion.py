@@ -105,6 +105,8 @@ def expand(vertices, faces, _alpha, _scale, eps: float = EPS_S0, activated: bool
 class _UpdateAlpha(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vertices, faces, alpha_raw):
+        if not vertices.is_cuda:
+            raise RuntimeError("gms_b200.update_alpha: CUDA tensors required (no CPU path in the product)")
         L = _lib.lib()
         dev = vertices.device
         v, a = _f32(vertices.detach()), _f32(alpha_raw.detach())
@@ -117,11 +119,10 @@ class _UpdateAlpha(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(L.gms_expand_forward(C.byref(args), _stream(dev)), "gms_expand_forward")
         ctx.save_for_backward(v, f, a, dummy_scale)
-        ctx.mark_non_differentiable(alpha)
         return alpha, tri, xyz
 
     @staticmethod
-    def backward(ctx, _ga, g_tri, g_xyz):
+    def backward(ctx, g_alpha, g_tri, g_xyz):
         L = _lib.lib()
         v, f, a, dummy = ctx.saved_tensors
         dev = v.device
@@ -137,12 +138,22 @@ class _UpdateAlpha(torch.autograd.Function):
         if g_tri is not None:
             dtri = dtri + g_tri
         dv = torch.zeros_like(v).index_add_(0, f.reshape(-1), dtri.reshape(-1, 3))
+        if g_alpha is not None:
+            # pc.alpha is consumed directly by renderer/gaussian_animated_renderer/__init__.py:61-64 and
+            # flame_gaussian_renderer:60 (`torch.matmul(pc.alpha, triangles)`): backward of
+            # alpha = r / sum(r), r = relu(_alpha) + 1e-8 (gaussian_mesh_model.py:166-167).  Rare path, ATen ops.
+            r = torch.relu(a) + 1e-8
+            ssum = r.sum(dim=-1, keepdim=True)
+            alpha = r / ssum
+            da = da + (g_alpha - (g_alpha * alpha).sum(dim=-1, keepdim=True)) / ssum * (a > 0).to(a.dtype)
         return dv, None, da
 
 
 class _PrepareScalingRot(torch.autograd.Function):
     @staticmethod
     def forward(ctx, triangles, scale_raw, K, eps):
+        if not triangles.is_cuda:
+            raise RuntimeError("gms_b200.prepare_scaling_rot: CUDA tensors required (no CPU path in the product)")
         L = _lib.lib()
         dev = triangles.device
         t, s = _f32(triangles.detach()), _f32(scale_raw.detach())
@@ -176,7 +187,7 @@ class _PrepareScalingRot(torch.autograd.Function):
 
 
 def update_alpha_op(vertices, faces, _alpha):
-    """-> (alpha [F,K,3] (no grad), triangles [F,3,3], xyz [P,3]); gaussian_mesh_model.py:153-169."""
+    """-> (alpha [F,K,3], triangles [F,3,3], xyz [P,3]), all differentiable; gaussian_mesh_model.py:153-169."""
     return _UpdateAlpha.apply(vertices, faces, _alpha)
 
 
