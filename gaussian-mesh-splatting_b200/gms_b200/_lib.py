@@ -42,7 +42,8 @@ class RasterOutputs(C.Structure):
 
 class RasterSaved(C.Structure):
     _fields_ = [("geom", C.c_void_p), ("binning", C.c_void_p), ("image", C.c_void_p),
-                ("num_rendered", C.c_int64), ("num_visible", C.c_int64)]
+                ("num_rendered", C.c_int64), ("num_visible", C.c_int64), ("binning_capacity", C.c_int64),
+                ("flags", C.c_int32)]
 
 
 class RasterGrads(C.Structure):
@@ -105,18 +106,19 @@ class FrameArgs(C.Structure):
                 ("d_vertices", C.c_void_p), ("d_alpha_raw", C.c_void_p), ("d_scale_raw", C.c_void_p),
                 ("d_features", C.c_void_p), ("d_opacity_raw", C.c_void_p),
                 ("settings", RasterSettings), ("gt", C.c_void_p), ("lambda_dssim", C.c_float), ("loss", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("num_rendered", C.POINTER(C.c_int64))]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("num_rendered", C.POINTER(C.c_int64)),
+                ("binning_capacity", C.c_int64), ("n_host_mapped", C.c_void_p)]
 
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
 
 # every symbol include/gms_b200.h declares (tests/test_abi.py checks the library exports all of them)
-ABI_SYMBOLS = ["gms_scratch_bytes", "gms_binning_bytes", "gms_rasterize_forward", "gms_rasterize_backward",
+ABI_SYMBOLS = ["gms_scratch_bytes", "gms_binning_bytes", "gms_rasterize_forward", "gms_rasterize_forward_nosync", "gms_rasterize_backward",
                "gms_mark_visible", "gms_debug_get_views", "gms_debug_unpack", "gms_expand_forward",
                "gms_expand_backward", "gms_last_error", "gms_version", "gms_launch_count", "gms_set_option",
                "gms_kernel_times", "gms_loss_scratch_bytes", "gms_l1_ssim_loss", "gms_adam_step",
                "gms_frame_workspace_bytes", "gms_train_frame", "gms_points_expand_forward",
-               "gms_points_prepare_vertices"]
+               "gms_points_prepare_vertices", "gms_image_quantize", "gms_image_dequantize"]
 
 _lib = None
 
@@ -143,6 +145,8 @@ def lib():
     L.gms_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.gms_rasterize_forward.argtypes = [C.POINTER(RasterSettings), C.POINTER(RasterInputs), C.POINTER(RasterOutputs),
                                         ALLOC_FN, C.c_void_p, C.POINTER(RasterSaved), C.c_void_p]
+    L.gms_rasterize_forward_nosync.argtypes = [C.POINTER(RasterSettings), C.POINTER(RasterInputs), C.POINTER(RasterOutputs),
+                                               ALLOC_FN, C.c_void_p, C.POINTER(RasterSaved), C.c_int64, C.c_void_p, C.c_void_p]
     L.gms_rasterize_backward.argtypes = [C.POINTER(RasterSettings), C.POINTER(RasterInputs), C.c_void_p,
                                          C.POINTER(RasterSaved), C.c_void_p, C.c_void_p, C.POINTER(RasterGrads),
                                          C.c_void_p]
@@ -158,6 +162,8 @@ def lib():
     L.gms_adam_step.argtypes = [C.POINTER(AdamArgs), C.c_void_p]
     L.gms_points_expand_forward.argtypes = [C.POINTER(PointsArgs), C.c_void_p]
     L.gms_points_prepare_vertices.argtypes = [C.POINTER(PointsVerticesArgs), C.c_void_p]
+    L.gms_image_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.gms_image_dequantize.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.gms_frame_workspace_bytes.restype = C.c_size_t
     L.gms_frame_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.gms_train_frame.argtypes = [C.POINTER(FrameArgs), ALLOC_FN, C.c_void_p, C.c_void_p]

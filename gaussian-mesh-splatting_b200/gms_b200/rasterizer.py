@@ -157,7 +157,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         last_num_rendered = int(saved.num_rendered)
         if KEEP_DEBUG:
             global last_debug
-            last_debug = dict(scratch=scratch, num_rendered=int(saved.num_rendered), P=P, W=W, H=H, radii=radii)
+            last_debug = dict(scratch=scratch, num_rendered=int(saved.num_rendered), P=P, W=W, H=H, radii=radii,
+                              bin_state=(int(saved.binning_capacity), int(saved.flags)))
         ctx.sh_sink = None
         if DIRECT_SH_GRAD and sh is not None and shs is not None and sh.is_leaf and sh.grad is not None and \
                 sh.grad.is_contiguous() and sh.grad.shape == shs.shape and sh.grad.dtype == torch.float32 and \
@@ -165,6 +166,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             ctx.sh_sink = sh.grad
         ctx.raster_settings = raster_settings
         ctx.num_rendered = int(saved.num_rendered)
+        ctx.bin_state = (int(saved.binning_capacity), int(saved.flags))
         ctx.scratch = scratch
         ctx.keep = keep
         ctx.dims = (P, M)
@@ -188,6 +190,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         b = ctx.scratch.bufs
         saved.geom = _ptr(b.get(_lib.BUF_GEOM)); saved.binning = _ptr(b.get(_lib.BUF_BINNING)); saved.image = _ptr(b.get(_lib.BUF_IMAGE))
         saved.num_rendered = ctx.num_rendered
+        saved.binning_capacity, saved.flags = ctx.bin_state
         if grad_out_color is None:
             grad_out_color = torch.zeros((3, int(rs.image_height), int(rs.image_width)), dtype=torch.float32, device=device)
         gcol = _dev_f32(grad_out_color, device)
@@ -253,14 +256,18 @@ class GaussianRasterizer(nn.Module):
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, rs)
 
 
-def forward_debug_state(ctx_scratch: _Scratch, num_rendered: int, P: int, W: int, H: int, radii: torch.Tensor):
-    """Parity-test helper: unpack the library's intermediate buffers into torch tensors (stock layouts)."""
+def forward_debug_state(ctx_scratch: _Scratch, num_rendered: int, P: int, W: int, H: int, radii: torch.Tensor, bin_state=None):
+    """Parity-test helper: unpack the library's intermediate buffers into torch tensors (stock layouts).
+    bin_state = (binning_capacity, flags) of the forward call (default: taken from last_debug)."""
+    if bin_state is None:
+        bin_state = (last_debug or {}).get("bin_state", (0, 0))
     L = _lib.lib()
     device = radii.device
     saved = _lib.RasterSaved()
     b = ctx_scratch.bufs
     saved.geom = _ptr(b.get(_lib.BUF_GEOM)); saved.binning = _ptr(b.get(_lib.BUF_BINNING)); saved.image = _ptr(b.get(_lib.BUF_IMAGE))
     saved.num_rendered = int(num_rendered)
+    saved.binning_capacity, saved.flags = int(bin_state[0]), int(bin_state[1])
     out = {}
     if P > 0:
         means2D = torch.zeros(P, 2, device=device); depths = torch.zeros(P, device=device)
@@ -288,8 +295,20 @@ def forward_debug_state(ctx_scratch: _Scratch, num_rendered: int, P: int, W: int
         out["cov3D"] = view(v.cov3D, 6 * P, torch.float32).view(P, 6)
         out["tiles_touched"] = view(v.tiles_touched, P, torch.int32)
     out["point_list"] = view(v.point_list, int(num_rendered), torch.int32)
-    out["tile_keys"] = view(v.tile_keys, int(num_rendered), torch.int32)
     out["ranges"] = view(v.ranges, 2 * T, torch.int32).view(T, 2)
+    if v.tile_keys:
+        out["tile_keys"] = view(v.tile_keys, int(num_rendered), torch.int32)
+    else:   # counting binning materialises no key array: the tile of every list position follows from the ranges
+        cnt = (out["ranges"][:, 1] - out["ranges"][:, 0]).long()
+        start = out["ranges"][:, 0].long()
+        tk = torch.full((int(num_rendered),), -1, dtype=torch.int32, device=device)
+        tiles_ne = torch.nonzero(cnt > 0).flatten()
+        if tiles_ne.numel():
+            c = cnt[tiles_ne]
+            pos = torch.repeat_interleave(start[tiles_ne], c) + \
+                (torch.arange(int(c.sum()), device=device) - torch.repeat_interleave(torch.cumsum(c, 0) - c, c))
+            tk[pos] = torch.repeat_interleave(tiles_ne, c).int()
+        out["tile_keys"] = tk
     out["final_T"] = view(v.final_T, W * H, torch.float32).view(H, W)
     out["n_contrib"] = view(v.n_contrib, W * H, torch.int32).view(H, W)
     return out

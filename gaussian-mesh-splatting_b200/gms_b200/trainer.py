@@ -50,9 +50,15 @@ class NativeFrame:
     """One training frame through gms_train_frame: expansion, rasterizer, loss and both backward passes issued from ONE C
     call on the current stream -- no autograd graph, no per-op Python.  Gradients land in the parameters' preallocated
     .grad views (FlatAdam's flat buffer); intermediates live in a persistent workspace, rasterizer scratch in grow-only
-    buffers served through the allocation callback."""
+    buffers served through the allocation callback.
 
-    def __init__(self, model: MeshGaussianModel, width: int, height: int, lambda_dssim: float = 0.2):
+    sync_free (default): only the FIRST frame learns N through the stock-style 4-byte read-back; from then on the binning
+    region is capacity-sized (grow-only, 1.5x the largest N seen + slack), N stays on the device and is mirrored by the
+    binning kernel into mapped pinned host memory (`n_host`: N, overflow flag) that the host polls WITHOUT synchronising.
+    A frame whose N exceeds the capacity renders the background with zero gradients and raises the flag; the next run()
+    grows the region, counts the event in `overflows` and carries on."""
+
+    def __init__(self, model: MeshGaussianModel, width: int, height: int, lambda_dssim: float = 0.2, sync_free: bool = True):
         import ctypes as C
         from . import _lib
         assert model._features is not None, "NativeFrame needs packed SH features"
@@ -63,6 +69,11 @@ class NativeFrame:
         self.ws = torch.empty(int(_lib.lib().gms_frame_workspace_bytes(P, self.W, self.H)), dtype=torch.uint8, device=dev)
         self.loss = torch.zeros(3, dtype=torch.float32, device=dev)
         self.n_rendered = C.c_int64(0)
+        self.sync_free = bool(sync_free)
+        self.capacity = 0                       # duplicates the binning region is sized for (0: not known yet)
+        self.n_host = torch.zeros(2, dtype=torch.int32).pin_memory()     # written by k_bin_tiles: N, overflow flag
+        self.overflows = 0
+        self._check_model()
         scratch = {}
         self._scratch = scratch
 
@@ -78,9 +89,32 @@ class NativeFrame:
 
         self._cb = _lib.ALLOC_FN(_alloc)        # closure captures `scratch`/`dev` only (no reference cycle through self)
 
+    def _check_model(self):
+        """Raw pointers go straight to CUDA kernels: dtype / device / layout are checked here, once, instead of failing
+        as an illegal address later."""
+        m = self.model
+        if m.faces.dtype != torch.int64 or not m.faces.is_contiguous():
+            m.faces = m.faces.long().contiguous()
+        for name in ("vertices", "_alpha", "_scale", "_features", "_opacity"):
+            t = getattr(m, name)
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == self.dev):
+                raise RuntimeError(f"NativeFrame: model.{name} must be a contiguous float32 CUDA tensor on {self.dev}")
+            if t.grad is None or not t.grad.is_contiguous() or t.grad.device != self.dev:
+                raise RuntimeError(f"NativeFrame: model.{name}.grad must be a preallocated contiguous buffer (FlatAdam provides it)")
+        if m.faces.device != self.dev:
+            raise RuntimeError("NativeFrame: model.faces must live on the model's device")
+
+    @property
+    def last_num_rendered(self) -> int:
+        """N of the most recent frame whose binning kernel has run (no synchronisation: may lag by a frame)."""
+        return int(self.n_host[0]) if (self.sync_free and self.capacity > 0) else int(self.n_rendered.value)
+
     def run(self, cam: Camera, gt: torch.Tensor, bg: torch.Tensor) -> torch.Tensor:
         import ctypes as C
         from . import _lib
+        for t, what in ((gt, "gt"), (bg, "bg"), (cam.world_view_transform, "camera matrices"), (cam.camera_center, "camera centre")):
+            if not t.is_cuda or t.device != self.dev:
+                raise RuntimeError(f"NativeFrame.run: {what} must be on {self.dev}")
         if int(cam.image_width) != self.W or int(cam.image_height) != self.H or tuple(gt.shape[-2:]) != (self.H, self.W):
             raise ValueError(f"NativeFrame was sized for {self.W}x{self.H}; got a {cam.image_width}x{cam.image_height} camera")
         if not gt.is_contiguous() or gt.dtype != torch.float32:
@@ -100,9 +134,20 @@ class NativeFrame:
         a.gt, a.lambda_dssim, a.loss = gt.data_ptr(), self.lam, self.loss.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
         a.num_rendered = C.pointer(self.n_rendered)
+        first = self.capacity == 0
+        if self.sync_free and not first:
+            if int(self.n_host[1]) != 0:       # some earlier frame overflowed the binning region: grow before this one
+                self.overflows += 1
+                self.capacity = int(max(self.capacity, int(self.n_host[0])) * 1.5) + (1 << 20)
+                self.n_host[1] = 0
+            a.binning_capacity, a.n_host_mapped = self.capacity, self.n_host.data_ptr()
         with torch.cuda.device(self.dev):
             _lib.check(_lib.lib().gms_train_frame(C.byref(a), self._cb, None, torch.cuda.current_stream(self.dev).cuda_stream),
                        "gms_train_frame")
+        if self.sync_free and first:           # the one synchronising frame told us N
+            n = max(int(self.n_rendered.value), 0)
+            self.capacity = int(n * 1.5) + (1 << 20)
+            self.n_host[0] = n
         return self.loss[0]
 
 
@@ -152,7 +197,7 @@ class MeshTrainer:
                 self._frame = NativeFrame(self.model, cam.image_width, cam.image_height, self.lambda_dssim)
             loss = self._frame.run(cam, gt, self.bg)
             from . import rasterizer as _r
-            _r.last_num_rendered = int(self._frame.n_rendered.value)
+            _r.last_num_rendered = self._frame.last_num_rendered
             if loss_host is not None:
                 loss_host.copy_(loss.reshape(loss_host.shape), non_blocking=True)
                 if loss_ready is not None:

@@ -100,6 +100,8 @@ typedef struct gms_raster_saved {
     void* image;
     int64_t num_rendered;   /* N = number of (tile, Gaussian) duplicates */
     int64_t num_visible;    /* Gaussians with radii > 0 (statistics; may be -1 if not computed) */
+    int64_t binning_capacity; /* duplicates the binning region was sized for (== num_rendered on the synchronising call) */
+    int32_t flags;          /* bit 0: the binning region holds the point list only (counting binning, the default) */
 } gms_raster_saved;
 
 /* Gradients produced by backward (caller-allocated; NULL where the corresponding input was NULL). */
@@ -124,6 +126,17 @@ size_t gms_binning_bytes(int64_t num_rendered, int32_t P);
 int gms_rasterize_forward(const gms_raster_settings* settings, const gms_raster_inputs* in,
                           const gms_raster_outputs* out, gms_alloc_fn alloc, void* alloc_user,
                           gms_raster_saved* saved, void* cuda_stream);
+
+/* The same forward WITHOUT the stock pipeline's per-frame host synchronisation ([upstream rasterizer_impl.cu:
+ * cudaMemcpy(&num_rendered, ...)]): the caller sizes the binning region for `binning_capacity` duplicates, N is computed
+ * and consumed on the device, saved->num_rendered is -1.  `n_host_mapped` (optional) is device-accessible pinned HOST
+ * memory [2]: the binning kernel stores N and an overflow flag there, readable later without a sync.  If N exceeds the
+ * capacity the frame degrades to the background image with zero gradients (flag = 1) -- grow and re-run.  No allocation,
+ * no blocking call: the whole frame can be captured in a CUDA graph. */
+int gms_rasterize_forward_nosync(const gms_raster_settings* settings, const gms_raster_inputs* in,
+                                 const gms_raster_outputs* out, gms_alloc_fn alloc, void* alloc_user,
+                                 gms_raster_saved* saved, int64_t binning_capacity, uint32_t* n_host_mapped,
+                                 void* cuda_stream);
 
 /* dL_dout_invdepth may be NULL (train.py never puts a loss on render_pkg["depth"]). */
 int gms_rasterize_backward(const gms_raster_settings* settings, const gms_raster_inputs* in,
@@ -282,10 +295,22 @@ typedef struct gms_frame_args {
     float lambda_dssim;
     float* loss;                /* device [3]: loss, L1, SSIM */
     void* workspace; size_t workspace_bytes;
-    int64_t* num_rendered;      /* host, optional */
+    int64_t* num_rendered;      /* host, optional (-1 on the sync-free path) */
+    int64_t binning_capacity;   /* > 0: sync-free frame (gms_rasterize_forward_nosync semantics); 0: stock-style, one 4-byte D2H */
+    uint32_t* n_host_mapped;    /* optional mapped pinned host [2]: N, overflow flag */
 } gms_frame_args;
 size_t gms_frame_workspace_bytes(int32_t P, int32_t W, int32_t H);
 int gms_train_frame(const gms_frame_args* a, gms_alloc_fn alloc, void* alloc_user, void* cuda_stream);
+
+/* ---- image sink / source ---------------------------------------- */
+
+/* float [C,H,W] -> 8-bit interleaved rows, byte = clamp(x * 255 + 0.5, 0, 255) truncated: the device half of
+ * torchvision.utils.save_image (scripts/render_time_animated.py:86-87, scripts/render.py) in one pass.  Output row stride is
+ * row_prefix + W*C bytes; row_prefix = 1 reserves PNG's filter byte (written 0), 0 gives plain HWC (PPM / raw video). */
+int gms_image_quantize(const float* chw, uint8_t* out, int32_t C, int32_t H, int32_t W, int32_t row_prefix, void* cuda_stream);
+/* 8-bit image ([H,W,C] if src_is_hwc else [C,H,W]) -> float [C,H,W] = byte / 255 (ToTensor / PILtoTorch,
+ * utils/general_utils.py:105-112): ground-truth images can stay 8-bit on the host and on the device. */
+int gms_image_dequantize(const uint8_t* src, int32_t src_is_hwc, float* chw, int32_t C, int32_t H, int32_t W, void* cuda_stream);
 
 /* ---- misc ------------------------------------------------------------------------------------- */
 const char* gms_last_error(void);

@@ -169,6 +169,69 @@ def test_sort_implementations_give_the_stock_order(impl, P, W, H):
     assert_forward_parity(st, color, radii, invd, state)
 
 
+@pytest.mark.parametrize("bin_impl,sort_impl", [(1, 0), (1, 1), (0, 0)])
+@pytest.mark.parametrize("P,W,H,scale_mu", [(50000, 640, 480, -2.4), (300, 48, 32, -2.4), (5000, 1920, 1080, -2.4), (400, 800, 608, -0.7)])
+def test_binning_implementations_give_the_stock_order(bin_impl, sort_impl, P, W, H, scale_mu):
+    """Cooperative counting binning (gms_binning.cuh, default) and the round-1 emit + radix-sort path: identical,
+    oracle-exact (tile, depth bits, index) lists.  The last case has huge splats (rectangles of hundreds of tiles: the
+    warp-cooperative branches) and long lists."""
+    S, g = _case(P, W, H, seed=P + bin_impl, extent=1.1, scale_mu=scale_mu)
+    old_b, old_s = _lib.set_option("bin_impl", bin_impl), _lib.set_option("sort_impl", sort_impl)
+    try:
+        color, radii, invd, state, _ = run_gpu(S, g)
+    finally:
+        _lib.set_option("bin_impl", old_b); _lib.set_option("sort_impl", old_s)
+    st, _ = run_oracle(S, g)
+    assert_forward_parity(st, color, radii, invd, state)
+
+
+def test_nosync_forward_matches_and_overflow_degrades_to_background():
+    """gms_rasterize_forward_nosync through the raw C ABI: with enough capacity it equals the synchronising call bit for
+    bit and reports N through the mapped host word; with too little it raises the overflow flag and renders the
+    background (never writes past the region)."""
+    import ctypes as C
+    from gms_b200 import rasterizer as R
+    S, g = _case(20000, 400, 300, seed=9)
+    color, radii, invd, state, _ = run_gpu(S, g)
+    N = state["num_rendered"]
+    dev = torch.device("cuda")
+    from gpu_helpers import gpu_settings
+    rs = gpu_settings(S)
+    keep = []
+    s = R._settings_struct(rs, dev, keep)
+    t = {k: v.cuda().float().contiguous() for k, v in g.items()}
+    P = t["means3D"].shape[0]
+    i = R._inputs_struct(P, 16, t["means3D"], t["opacities"], t["shs"], None, t["scales"], t["rotations"], None)
+    for cap, expect_overflow in ((N + 5, False), (N, False), (N // 2, True)):
+        out_c = torch.full((3, 300, 400), -1.0, device=dev); out_r = torch.zeros(P, dtype=torch.int32, device=dev)
+        out_d = torch.full((1, 300, 400), -1.0, device=dev)
+        o = _lib.RasterOutputs(out_c.data_ptr(), out_r.data_ptr(), out_d.data_ptr())
+        bufs = {}
+        guard = {}
+
+        def _alloc(user, which, nbytes):
+            b = torch.zeros(int(nbytes) + 4096, dtype=torch.uint8, device=dev)
+            b[int(nbytes):] = 0xAB                              # canary behind the requested region
+            bufs[int(which)] = b; guard[int(which)] = int(nbytes)
+            return b.data_ptr()
+
+        cb = _lib.ALLOC_FN(_alloc)
+        saved = _lib.RasterSaved()
+        n_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        _lib.check(_lib.lib().gms_rasterize_forward_nosync(C.byref(s), C.byref(i), C.byref(o), cb, None, C.byref(saved), cap,
+                                                           n_host.data_ptr(), torch.cuda.current_stream().cuda_stream), "nosync")
+        torch.cuda.synchronize()
+        assert int(saved.num_rendered) == -1 and int(saved.flags) & 1 and int(saved.binning_capacity) == cap
+        assert int(n_host[0]) == N and int(n_host[1]) == int(expect_overflow)
+        for which, nb in guard.items():
+            assert bool((bufs[which][nb:] == 0xAB).all()), f"scratch region {which} overrun"
+        if expect_overflow:
+            bg = torch.tensor(np.asarray(S.bg, np.float32), device=dev)
+            assert torch.equal(out_c, bg[:, None, None].expand_as(out_c)) and float(out_d.abs().max()) == 0.0
+        else:
+            assert torch.equal(out_c.cpu(), torch.tensor(color)) and torch.equal(out_r.cpu(), torch.tensor(radii))
+
+
 @pytest.mark.parametrize("P,deg", [(4001, 3), (77, 1), (12345, 0)])
 def test_sh_tile_staging_equals_direct_access(P, deg):
     """Option "sh_staged": SH rows (and their gradient rows) through the per-warp shared-memory tile vs per-lane global

@@ -159,3 +159,38 @@ def test_native_frame_equals_autograd_path():
         assert abs(l1 - l2) <= 2e-4 * abs(l2)
     np.testing.assert_allclose(ma._opacity.detach().cpu().numpy(), mb._opacity.detach().cpu().numpy(), rtol=1e-3, atol=2e-3)
     np.testing.assert_allclose(ma._features.detach().cpu().numpy(), mb._features.detach().cpu().numpy(), rtol=1e-3, atol=2e-3)
+
+
+def test_sync_free_native_frame_equals_synchronising_frame():
+    """NativeFrame(sync_free=True): after the first (synchronising) frame no host sync happens, N is polled from mapped
+    pinned memory, and losses / gradients / parameters are bit-identical to the stock-style frame."""
+    from gms_b200.trainer import NativeFrame
+    p = scenes.init_mesh_gaussians(*scenes.icosphere(4), K=3, seed=8)
+    cams = [c.to("cuda") for c in scenes.ring_cameras(5, 2.5, 352, 256)]
+    bg = torch.ones(3, device="cuda")
+    gt_model = MeshGaussianModel.from_params(scenes.init_mesh_gaussians(*scenes.icosphere(4), K=3, seed=79), "cuda")
+    with torch.no_grad():
+        gts = [render_frame(gt_model, c, bg)[0].clamp(0, 1).contiguous() for c in cams]
+    res = []
+    for sync_free in (True, False):
+        m = MeshGaussianModel.from_params(p, "cuda", packed_features=True)
+        opt = FlatAdam(mesh_model_groups(m))
+        fr = NativeFrame(m, 352, 256, sync_free=sync_free)
+        losses_, ns = [], []
+        for s in range(7):
+            losses_.append(fr.run(cams[s % 5], gts[s % 5], bg).clone())
+            torch.cuda.synchronize()
+            ns.append(fr.last_num_rendered)
+            opt.step(zero_end=opt.ends[0])
+        res.append((torch.stack(losses_).cpu(), ns, opt.p.clone().cpu(), fr))
+    (la, na, pa, fa), (lb, nb, pb, fb) = res
+    assert fa.capacity > 0 and fa.overflows == 0 and fb.capacity == 0
+    assert na == nb and min(na) > 0
+    assert torch.equal(la, lb)
+    np.testing.assert_allclose(pa.numpy(), pb.numpy(), rtol=0, atol=1e-6)       # vertex gradients: atomics, order may differ
+    # forced overflow: capacity below N -> flag, background frame, then automatic growth
+    fa.capacity = max(na) // 3
+    fa.run(cams[0], gts[0], bg); torch.cuda.synchronize()
+    assert int(fa.n_host[1]) == 1
+    fa.run(cams[0], gts[0], bg); torch.cuda.synchronize()
+    assert fa.overflows == 1 and int(fa.n_host[1]) == 0 and fa.last_num_rendered == na[0]
