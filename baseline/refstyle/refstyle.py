@@ -102,7 +102,7 @@ class _RefStyleRasterize(torch.autograd.Function):
             return t.data_ptr()
 
         cb = _abi.ALLOC_FN(_alloc)
-        o = _abi.RasterOutputs(color.data_ptr(), radii.data_ptr(), invdepth.data_ptr())
+        o = _abi.RasterOutputs(color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), 0)
         saved = _abi.RasterSaved()
         with torch.cuda.device(dev):
             _check(L.refstyle_rasterize_forward(C.byref(s), C.byref(i), C.byref(o), cb, None, C.byref(saved),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "gms_kernels.cu")
 DEPS = [os.path.join(HERE, "csrc", f) for f in ("gms_kernels.cu", "gms_common.cuh", "gms_preprocess.cuh",
-                                                "gms_expand.cuh", "gms_composite.cuh", "gms_composite2.cuh", "gms_composite3.cuh", "gms_composite4.cuh", "gms_loss.cuh", "gms_sort.cuh", "gms_binning.cuh", "gms_image.cuh")] + \
+                                                "gms_expand.cuh", "gms_composite_common.cuh", "gms_composite_fwd.cuh", "gms_composite_bwd.cuh", "gms_loss.cuh", "gms_sort.cuh", "gms_binning.cuh", "gms_image.cuh")] + \
        [os.path.join(HERE, "..", "include", "gms_b200.h")]
 OUT = os.path.join(HERE, "gms_b200", "libgms_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -8,14 +8,19 @@
 // tile id -- no keys have to be materialised and nothing has to be sorted again:
 //
 //   phase 1  every warp owns a contiguous slice of the depth order and counts, per tile, how many of its Gaussians cover
-//            it (16-bit counters in the warp's own shared-memory row, two tiles per 32-bit word; order does not matter
-//            here, so the lanes walk their own rectangles in parallel);  a CTA-level exclusive scan over the warps'
-//            rows turns them into warp offsets and yields the CTA's per-tile count  M[cta][tile]          -> grid.sync
-//   phase 2a one thread per tile scans M[.][tile] over the CTAs (exclusive, in place) and writes total[tile]  -> grid.sync
-//   phase 2b every CTA scans total[] (T <= 16 K entries, block scan) into tile starts; base[tile] = start + M[cta][tile]
-//            lives in shared memory; CTA 0 writes ranges[] and N.  N > capacity: overflow flag, empty ranges, no writes.
-//   phase 3  every warp walks its slice again IN ORDER, one Gaussian per step with the lanes over its tiles, and writes
+//            it (16-bit counters in the warp's own shared-memory row, two tiles per 32-bit word);  a CTA-level
+//            exclusive scan over the warps' rows turns them into warp offsets and yields the CTA's per-tile count
+//            M[cta][tile]                                                                                  -> grid.sync
+//   phase 2a per tile, exclusive scan of M[.][tile] over the CTAs (in place) and total[tile]              -> grid.sync
+//   phase 2b every CTA scans total[] (block scan in shared memory) into tile starts; base[tile] = start + M[cta][tile]
+//            stays in shared memory; CTA 0 writes ranges[] and N.  N > capacity: overflow flag, empty ranges, no writes.
+//   phase 3  every warp walks its slice again IN ORDER and writes
 //            point_list[base[tile] + row[warp][tile]++] = Gaussian id.
+// Both walks are DENSE over (Gaussian, tile) pairs: a batch of 32 Gaussians is loaded one per lane (ids and rectangles
+// two / one batch ahead), a warp scan of the rectangle areas numbers the batch's pairs Gaussian-major, and every step hands
+// 32 consecutive pairs to the 32 lanes (owner found by a 5-step shuffle search) -- full lanes whatever the rectangle sizes.
+// In phase 3 the lanes of a step that hit the same tile (different Gaussians, lane order = depth order) are ranked with
+// match.any and served by ONE shared-memory atomic; steps follow each other in program order, so slots come out in depth order.
 //
 // The result is bit-identical to the stock (tile << 32 | depth) sort (tests/test_gpu_parity.py).  Device-side N, no host
 // synchronisation, no scan over P, no key arrays: at 1M Gaussians / 1080p it replaces 0.016 (scan) + 0.04 (emit) + 0.125
@@ -54,17 +59,78 @@ static inline int gms_bin_warps(int T, size_t budget) {
     return 0;
 }
 
-__device__ __forceinline__ void gms_bin_unpack(const uint2 r, int& x0, int& y0, int& w, int& nt) {
-    x0 = (int)(r.x & 0xffffu); y0 = (int)(r.x >> 16);
+__device__ __forceinline__ void gms_bin_unpack(const uint2 r, int gx, int& t00, int& w, int& nt) {
+    const int x0 = (int)(r.x & 0xffffu), y0 = (int)(r.x >> 16);
     w = (int)(r.y & 0xffffu) - x0;
     nt = w * ((int)(r.y >> 16) - y0);
+    t00 = y0 * gx + x0;
+    if (nt <= 0) { nt = 0; w = 1; }
+}
+
+// One pass over the warp's slice [j_lo, j_hi) of the depth order, 32 (Gaussian, tile) pairs per step.
+// PLACE = false: count into `row`.  PLACE = true: ordered slots from `row`, ids to point_list.
+template <bool PLACE>
+__device__ __forceinline__ void gms_bin_walk(const GmsBinArgs& a, uint32_t j_lo, uint32_t j_hi, int lane, uint32_t* row, const uint32_t* base) {
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lt = (1u << lane) - 1u;
+    // software pipeline: ids two batches ahead, rectangles one batch ahead
+    uint32_t g_cur = 0, g_nx = 0;
+    uint2 r_cur = make_uint2(0u, 0u);
+    if (j_lo + lane < j_hi) { g_cur = a.order[j_lo + lane]; r_cur = a.rect[g_cur]; }
+    if (j_lo + 32 + lane < j_hi) g_nx = a.order[j_lo + 32 + lane];
+    for (uint32_t j0 = j_lo; j0 < j_hi; j0 += 32) {
+        const uint32_t g = g_cur;
+        int t00, w, nt;
+        gms_bin_unpack((j0 + lane < j_hi) ? r_cur : make_uint2(0u, 0u), a.gx, t00, w, nt);
+        // prefetch
+        g_cur = g_nx;
+        r_cur = (j0 + 32 + lane < j_hi) ? a.rect[g_cur] : make_uint2(0u, 0u);
+        g_nx = (j0 + 64 + lane < j_hi) ? a.order[j0 + 64 + lane] : 0u;
+        // number the batch's pairs Gaussian-major
+        int inc = nt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += y; }
+        const int tot = __shfl_sync(FULL, inc, 31);
+        const int exc = inc - nt;
+        for (int p0 = 0; p0 < tot; p0 += 32) {
+            const int p = p0 + lane;
+            const bool active = p < tot;
+            int lo = 0;         // owner = first lane whose inclusive prefix exceeds p
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) { const int v = __shfl_sync(FULL, inc, lo + st - 1); if (v <= p) lo += st; }
+            const int owner = lo & 31;
+            const int k = p - __shfl_sync(FULL, exc, owner);
+            const int t0s = __shfl_sync(FULL, t00, owner), ws = __shfl_sync(FULL, w, owner);
+            const int yy = (int)(((float)k + 0.5f) * __frcp_rn((float)ws));      // exact floor(k / ws) for k < 2^20
+            const int t = t0s + yy * a.gx + (k - yy * ws);
+            const int sh = (t & 1) * 16;
+            if (!PLACE) {
+                if (active) atomicAdd(&row[t >> 1], 1u << sh);
+            } else {
+                const uint32_t gs = __shfl_sync(FULL, g, owner);
+                const uint32_t peers = __match_any_sync(FULL, active ? (uint32_t)t : (0x40000000u | (uint32_t)lane));
+                const int leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if (active && lane == leader) old = atomicAdd(&row[t >> 1], (uint32_t)__popc(peers) << sh);
+                old = __shfl_sync(FULL, old, leader);
+                if (active) {
+                    const uint32_t pos = base[t] + ((old >> sh) & 0xffffu) + (uint32_t)__popc(peers & lt);
+                    a.point_list[pos] = gs;
+                    if (a.tile_keys) a.tile_keys[pos] = (uint32_t)t;
+                }
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(512, 1) k_bin_tiles(GmsBinArgs a) {
     extern __shared__ uint32_t bin_smem[];
+    __shared__ uint32_t s_part[512];
+    __shared__ uint32_t s_grp[16][64];
+    __shared__ uint32_t s_n;
     cg::grid_group grid = cg::this_grid();
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T = a.T, words = (T + 1) >> 1;
+    const int T = a.T, words = (T + 1) >> 1, G = (int)gridDim.x;
     uint32_t* rows = bin_smem;                          // [W][words]
     uint32_t* base = bin_smem + (size_t)W * words;      // [T]
     uint32_t* row = rows + (size_t)warp * words;
@@ -76,84 +142,76 @@ __global__ void __launch_bounds__(512, 1) k_bin_tiles(GmsBinArgs a) {
     const uint32_t j_lo = min(gw * per, nvis), j_hi = min(j_lo + per, nvis);
     __syncthreads();
 
-    // ---- phase 1: unordered counting
-    for (uint32_t j0 = j_lo; j0 < j_hi; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        int x0 = 0, y0 = 0, w = 0, nt = 0;
-        if (j < j_hi) gms_bin_unpack(a.rect[a.order[j]], x0, y0, w, nt);
-        const bool big = nt >= 64;
-        if (!big) {
-            int t = y0 * a.gx + x0, x = 0;
-            for (int k = 0; k < nt; k++) {
-                atomicAdd(&row[t >> 1], 1u << ((t & 1) * 16));
-                if (++x == w) { x = 0; t += a.gx - w + 1; } else t++;
-            }
-        }
-        uint32_t m = __ballot_sync(0xffffffffu, big);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const int x0s = __shfl_sync(0xffffffffu, x0, src), y0s = __shfl_sync(0xffffffffu, y0, src);
-            const int ws = __shfl_sync(0xffffffffu, w, src), nts = __shfl_sync(0xffffffffu, nt, src);
-            for (int k = lane; k < nts; k += 32) {
-                const int yy = k / ws, t = (y0s + yy) * a.gx + x0s + (k - yy * ws);
-                atomicAdd(&row[t >> 1], 1u << ((t & 1) * 16));
-            }
-        }
-    }
+    // ---- phase 1: counting
+    gms_bin_walk<false>(a, j_lo, j_hi, lane, row, nullptr);
     __syncthreads();
     // warps' rows -> exclusive offsets inside the CTA; CTA count per tile -> M
-    for (int i = threadIdx.x; i < words; i += blockDim.x) {
-        uint32_t run = 0;       // two 16-bit lanes at once; a CTA's count of one tile stays below 65536 (host checks per * W)
-        for (int wq = 0; wq < W; wq++) { const uint32_t c = rows[(size_t)wq * words + i]; rows[(size_t)wq * words + i] = run; run += c; }
+    {
         uint32_t* Mrow = a.M + (size_t)blockIdx.x * T;
-        Mrow[2 * i] = run & 0xffffu;
-        if (2 * i + 1 < T) Mrow[2 * i + 1] = run >> 16;
+        for (int i = threadIdx.x; i < words; i += blockDim.x) {
+            uint32_t run = 0;   // two 16-bit lanes at once; a CTA's count of one tile stays below 65536 (host checks P / grid)
+            for (int wq = 0; wq < W; wq++) { const uint32_t c = rows[(size_t)wq * words + i]; rows[(size_t)wq * words + i] = run; run += c; }
+            if (2 * i + 1 < T) *reinterpret_cast<uint2*>(Mrow + 2 * i) = make_uint2(run & 0xffffu, run >> 16);
+            else Mrow[2 * i] = run & 0xffffu;
+        }
     }
     grid.sync();
 
-    // ---- phase 2a: per tile, exclusive scan over the CTAs.  A chunk of 32 adjacent tiles per CTA round (coalesced rows of
-    // M); the W warps split the CTA axis, combine their partial sums through shared memory, then write the offsets.
+    // ---- phase 2a: per tile, exclusive scan over the CTAs.  64 adjacent tiles per CTA (two per lane: coalesced rows of M);
+    // the W warps split the CTA axis, combine their partial sums through shared memory, then write the offsets.
     {
-        __shared__ uint32_t s_grp[16][32];
-        const int G = (int)gridDim.x, cper = (G + W - 1) / W;
+        const int cper = (G + W - 1) / W;
         const int c_lo = min(warp * cper, G), c_hi = min(c_lo + cper, G);
-        for (int chunk = blockIdx.x; chunk * 32 < T; chunk += G) {
-            const int t = chunk * 32 + lane;
-            const bool ok = t < T;
-            uint32_t sum = 0;
-            for (int c = c_lo; c < c_hi; c += 8) {
-                uint32_t v[8];
+        for (int chunk = blockIdx.x; chunk * 64 < T; chunk += G) {
+            const int ta = chunk * 64 + lane, tb = ta + 32;
+            const bool oka = ta < T, okb = tb < T;
+            uint32_t suma = 0, sumb = 0;
+            for (int c = c_lo; c < c_hi; c += 4) {
+                uint32_t va[4], vb[4];
 #pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = (ok && c + u < c_hi) ? a.M[(size_t)(c + u) * T + t] : 0u;
+                for (int u = 0; u < 4; u++) {
+                    va[u] = (oka && c + u < c_hi) ? a.M[(size_t)(c + u) * T + ta] : 0u;
+                    vb[u] = (okb && c + u < c_hi) ? a.M[(size_t)(c + u) * T + tb] : 0u;
+                }
 #pragma unroll
-                for (int u = 0; u < 8; u++) sum += v[u];
+                for (int u = 0; u < 4; u++) { suma += va[u]; sumb += vb[u]; }
             }
-            s_grp[warp][lane] = sum;
+            s_grp[warp][lane] = suma; s_grp[warp][lane + 32] = sumb;
             __syncthreads();
-            uint32_t run = 0, tot = 0;
-            for (int q = 0; q < W; q++) { const uint32_t x = s_grp[q][lane]; if (q < warp) run += x; tot += x; }
-            for (int c = c_lo; c < c_hi; c += 8) {
-                uint32_t v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = (ok && c + u < c_hi) ? a.M[(size_t)(c + u) * T + t] : 0u;
-#pragma unroll
-                for (int u = 0; u < 8; u++) { if (ok && c + u < c_hi) a.M[(size_t)(c + u) * T + t] = run; run += v[u]; }
+            uint32_t runa = 0, tota = 0, runb = 0, totb = 0;
+            for (int q = 0; q < W; q++) {
+                const uint32_t xa = s_grp[q][lane], xb = s_grp[q][lane + 32];
+                if (q < warp) { runa += xa; runb += xb; }
+                tota += xa; totb += xb;
             }
-            if (ok && warp == 0) a.total[t] = tot;
+            for (int c = c_lo; c < c_hi; c += 4) {
+                uint32_t va[4], vb[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    va[u] = (oka && c + u < c_hi) ? a.M[(size_t)(c + u) * T + ta] : 0u;
+                    vb[u] = (okb && c + u < c_hi) ? a.M[(size_t)(c + u) * T + tb] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (oka && c + u < c_hi) a.M[(size_t)(c + u) * T + ta] = runa;
+                    if (okb && c + u < c_hi) a.M[(size_t)(c + u) * T + tb] = runb;
+                    runa += va[u]; runb += vb[u];
+                }
+            }
+            if (warp == 0) { if (oka) a.total[ta] = tota; if (okb) a.total[tb] = totb; }
             __syncthreads();
         }
     }
     grid.sync();
 
-    // ---- phase 2b: tile starts (every CTA, redundantly), base[] = start + this CTA's offset
-    __shared__ uint32_t s_part[512];
-    __shared__ uint32_t s_n;
+    // ---- phase 2b: tile starts (every CTA, redundantly, in shared memory); base[] = start + this CTA's offset
     {
+        for (int i = threadIdx.x; i < T; i += blockDim.x) base[i] = a.total[i];
+        __syncthreads();
         const int per_t = (T + blockDim.x - 1) / blockDim.x;
-        const int t0 = threadIdx.x * per_t, t1 = min(t0 + per_t, T);
+        const int t0 = min((int)threadIdx.x * per_t, T), t1 = min(t0 + per_t, T);
         uint32_t s = 0;
-        for (int t = t0; t < t1; t++) s += a.total[t];
+        for (int t = t0; t < t1; t++) s += base[t];
         s_part[threadIdx.x] = s;
         __syncthreads();
         if (warp == 0) {        // exclusive scan of <= 512 partials by one warp
@@ -172,10 +230,9 @@ __global__ void __launch_bounds__(512, 1) k_bin_tiles(GmsBinArgs a) {
         const uint32_t N = s_n;
         const bool overflow = N > a.capacity;
         uint32_t run = s_part[threadIdx.x];
-        const uint32_t* Mrow = a.M + (size_t)blockIdx.x * T;
         for (int t = t0; t < t1; t++) {
-            const uint32_t tot = a.total[t];
-            base[t] = run + Mrow[t];
+            const uint32_t tot = base[t];
+            base[t] = run;
             if (blockIdx.x == 0) a.ranges[t] = overflow ? make_int2(0, 0) : make_int2((int)run, (int)(run + tot));
             run += tot;
         }
@@ -183,35 +240,13 @@ __global__ void __launch_bounds__(512, 1) k_bin_tiles(GmsBinArgs a) {
             a.n_out[0] = N; a.n_out[1] = overflow ? 1u : 0u;
             if (a.n_host) { a.n_host[0] = N; a.n_host[1] = overflow ? 1u : 0u; }
         }
-        __syncthreads();
         if (overflow) return;       // uniform over the grid: no further grid.sync follows
+        __syncthreads();
+        const uint32_t* Mrow = a.M + (size_t)blockIdx.x * T;
+        for (int i = threadIdx.x; i < T; i += blockDim.x) base[i] += Mrow[i];
+        __syncthreads();
     }
 
-    // ---- phase 3: ordered placement (one Gaussian per step, lanes over its tiles)
-    for (uint32_t j0 = j_lo; j0 < j_hi; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        int x0 = 0, y0 = 0, w = 0, nt = 0;
-        uint32_t g = 0;
-        if (j < j_hi) { g = a.order[j]; gms_bin_unpack(a.rect[g], x0, y0, w, nt); }
-        const int t00 = y0 * a.gx + x0;
-        uint32_t m = __ballot_sync(0xffffffffu, nt > 0);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t gs = __shfl_sync(0xffffffffu, g, src);
-            const int t0s = __shfl_sync(0xffffffffu, t00, src);
-            const int ws = __shfl_sync(0xffffffffu, w, src), nts = __shfl_sync(0xffffffffu, nt, src);
-            const float inv = __frcp_rn((float)ws);
-            for (int k = lane; k < nts; k += 32) {
-                const int yy = (int)(((float)k + 0.5f) * inv);          // exact floor(k / ws) for k < 2^20
-                const int t = t0s + yy * a.gx + (k - yy * ws);
-                const int sh = (t & 1) * 16;
-                const uint32_t old = atomicAdd(&row[t >> 1], 1u << sh);
-                const uint32_t pos = base[t] + ((old >> sh) & 0xffffu);
-                a.point_list[pos] = gs;
-                if (a.tile_keys) a.tile_keys[pos] = (uint32_t)t;
-            }
-            __syncwarp();
-        }
-    }
+    // ---- phase 3: ordered placement
+    gms_bin_walk<true>(a, j_lo, j_hi, lane, row, base);
 }

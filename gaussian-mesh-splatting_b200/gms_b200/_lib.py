@@ -12,6 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgms_b200.so")
 
+FORWARD_ONLY = 1        # gms_raster_outputs.flags: no backward will follow (skip the survivor lists)
 GMS_OK, GMS_E_ARG, GMS_E_CUDA, GMS_E_ALLOC, GMS_E_UNSUPPORTED = 0, -1, -2, -3, -4
 BUF_GEOM, BUF_BINNING, BUF_IMAGE = 0, 1, 2
 
@@ -37,7 +38,7 @@ class RasterInputs(C.Structure):
 
 
 class RasterOutputs(C.Structure):
-    _fields_ = [("out_color", C.c_void_p), ("radii", C.c_void_p), ("out_invdepth", C.c_void_p)]
+    _fields_ = [("out_color", C.c_void_p), ("radii", C.c_void_p), ("out_invdepth", C.c_void_p), ("flags", C.c_int32)]
 
 
 class RasterSaved(C.Structure):
@@ -56,7 +57,7 @@ class DebugViews(C.Structure):
     _fields_ = [("means2D", C.c_void_p), ("depths", C.c_void_p), ("cov3D", C.c_void_p),
                 ("conic_opacity", C.c_void_p), ("rgb", C.c_void_p), ("clamped", C.c_void_p),
                 ("tiles_touched", C.c_void_p), ("point_list", C.c_void_p), ("tile_keys", C.c_void_p),
-                ("ranges", C.c_void_p), ("final_T", C.c_void_p), ("n_contrib", C.c_void_p)]
+                ("ranges", C.c_void_p), ("final_T", C.c_void_p), ("n_contrib", C.c_void_p), ("dgeom", C.c_void_p)]
 
 
 class ExpandArgs(C.Structure):

@@ -82,11 +82,15 @@ def load_gaussian_ply(path: str) -> Dict[str, torch.Tensor]:
     return out
 
 
-def save_gaussian_ply(path: str, xyz, features_dc, features_rest, opacity, scaling, rotation) -> None:
-    """Writer with the reference's property order / channel-major SH layout (scene/gaussian_model.py:177-216)."""
+def save_gaussian_ply(path: str, xyz, features_dc, features_rest, opacity, scaling, rotation, eps_s0: float = 1e-8) -> None:
+    """Writer with the reference's property order / channel-major SH layout (scene/gaussian_model.py:177-216).  A two-column
+    `scaling` (flat Gaussians, gs_flat / gs_points) gets the constant log(eps_s0) column prepended, as _save_ply does (:196-199),
+    so the file always carries scale_0..2."""
     t = lambda a: a.detach().cpu().float() if isinstance(a, torch.Tensor) else torch.as_tensor(a, dtype=torch.float32)
     xyz, fdc, frest, op, sc, rot = map(t, (xyz, features_dc, features_rest, opacity, scaling, rotation))
     P = xyz.shape[0]
+    if sc.dim() == 2 and sc.shape[1] == 2:
+        sc = torch.cat([torch.log(torch.ones(P, 1) * eps_s0), sc], dim=1)
     cols = [xyz, torch.zeros_like(xyz), fdc.transpose(1, 2).reshape(P, -1), frest.transpose(1, 2).reshape(P, -1), op.reshape(P, 1),
             sc.reshape(P, -1), rot.reshape(P, -1)]
     names = ["x", "y", "z", "nx", "ny", "nz"] + [f"f_dc_{i}" for i in range(cols[2].shape[1])] + \
@@ -115,9 +119,14 @@ def load_mesh_model(ply_path: str) -> MeshGaussianParams:
 
 
 def save_mesh_model(ply_path: str, model) -> None:
-    """Counterpart of GaussianMeshModel.save_ply (gaussian_mesh_model.py:189-209) for a gms_b200 MeshGaussianModel."""
+    """Counterpart of GaussianMeshModel.save_ply (gaussian_mesh_model.py:189-209) for a gms_b200 MeshGaussianModel.
+    model_params.pt holds what the reference's writer holds -- `_alpha`, `_scale`, `vertices` as nn.Parameters and
+    `triangles`, `faces` as tensors, all ON THE MODEL'S DEVICE, plus the `point_cloud` key -- because the reference's
+    load_ply (:211-225) uses them where they are (no .cuda()): a checkpoint written here loads in scripts/render.py."""
     model.update_alpha(); model.prepare_scaling_rot()
-    save_gaussian_ply(ply_path, model._xyz, model._features_dc, model._features_rest, model._opacity, model._scaling, model._rotation)
-    torch.save({"_alpha": model._alpha.detach().cpu(), "_scale": model._scale.detach().cpu(), "vertices": model.vertices.detach().cpu(),
-                "faces": model.faces.cpu(), "triangles": model.triangles.detach().cpu()},
+    save_gaussian_ply(ply_path, model._xyz, model._features_dc, model._features_rest, model._opacity, model._scaling, model._rotation,
+                      getattr(model, "eps_s0", 1e-8))
+    par = lambda t: torch.nn.Parameter(t.detach().clone().contiguous(), requires_grad=True)
+    torch.save({"_alpha": par(model._alpha), "_scale": par(model._scale), "point_cloud": None,
+                "triangles": model.triangles.detach().clone(), "vertices": par(model.vertices), "faces": model.faces.detach().clone()},
                ply_path.replace("point_cloud.ply", "model_params.pt"))

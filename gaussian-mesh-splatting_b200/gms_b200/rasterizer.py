@@ -137,7 +137,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         color = torch.empty((3, H, W), dtype=torch.float32, device=device)
         radii = torch.empty((P,), dtype=torch.int32, device=device)
         invdepth = torch.empty((1, H, W), dtype=torch.float32, device=device)
-        o = _lib.RasterOutputs(color.data_ptr(), radii.data_ptr(), invdepth.data_ptr())
+        # survivor lists for the backward pass are only worth writing when one can follow
+        wants_grad = any(ctx.needs_input_grad)         # (inside Function.forward grad mode is off: ask the ctx)
+        o = _lib.RasterOutputs(color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), 0 if wants_grad else _lib.FORWARD_ONLY)
         scratch = _Scratch(device)
         saved = _lib.RasterSaved()
         stream = torch.cuda.current_stream(device).cuda_stream
@@ -309,6 +311,8 @@ def forward_debug_state(ctx_scratch: _Scratch, num_rendered: int, P: int, W: int
                 (torch.arange(int(c.sum()), device=device) - torch.repeat_interleave(torch.cumsum(c, 0) - c, c))
             tk[pos] = torch.repeat_interleave(tiles_ne, c).int()
         out["tile_keys"] = tk
+    if v.dgeom and P > 0:
+        out["dgeom"] = view(v.dgeom, 12 * P, torch.float32).view(P, 12)     # meaningful after a backward call
     out["final_T"] = view(v.final_T, W * H, torch.float32).view(H, W)
     out["n_contrib"] = view(v.n_contrib, W * H, torch.int32).view(H, W)
     return out

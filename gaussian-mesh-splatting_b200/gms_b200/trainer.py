@@ -112,9 +112,10 @@ class NativeFrame:
     def run(self, cam: Camera, gt: torch.Tensor, bg: torch.Tensor) -> torch.Tensor:
         import ctypes as C
         from . import _lib
-        for t, what in ((gt, "gt"), (bg, "bg"), (cam.world_view_transform, "camera matrices"), (cam.camera_center, "camera centre")):
-            if not t.is_cuda or t.device != self.dev:
-                raise RuntimeError(f"NativeFrame.run: {what} must be on {self.dev}")
+        for t, what in ((gt, "gt"), (bg, "bg"), (cam.world_view_transform, "camera matrices"), (cam.full_proj_transform, "camera matrices"),
+                        (cam.camera_center, "camera centre")):
+            if not t.is_cuda or t.device != self.dev or t.dtype != torch.float32:
+                raise RuntimeError(f"NativeFrame.run: {what} must be float32 on {self.dev}")
         if int(cam.image_width) != self.W or int(cam.image_height) != self.H or tuple(gt.shape[-2:]) != (self.H, self.W):
             raise ValueError(f"NativeFrame was sized for {self.W}x{self.H}; got a {cam.image_width}x{cam.image_height} camera")
         if not gt.is_contiguous() or gt.dtype != torch.float32:
@@ -159,12 +160,13 @@ class MeshTrainer:
     fast=False : the reference's op sequence (two-step expansion + getters, ATen loss, torch.optim.Adam)."""
 
     def __init__(self, model: MeshGaussianModel, bg: torch.Tensor, lambda_dssim: float = 0.2, world: int = 1,
-                 rank: int = 0, optimizer_step: bool = True, fast: bool = True, native: bool = False):
+                 rank: int = 0, optimizer_step: bool = True, fast: bool = True, native: bool = False, sync_free: bool = True):
         self.model, self.bg, self.lambda_dssim = model, bg, lambda_dssim
         self.world, self.rank = world, rank
         self.optimizer_step = optimizer_step
         self.fast = fast
         self.native = native and fast       # native: the whole frame is one C call (NativeFrame), no autograd
+        self.sync_free = sync_free          # native frames after the first never synchronise with the host (NativeFrame)
         self._frame = None
         if fast:
             self.opt = FlatAdam(mesh_model_groups(model), world=world, rank=rank)   # sharded over the ranks when world > 1
@@ -194,7 +196,7 @@ class MeshTrainer:
         the loss every step waits only for the frame, and its next step's launch overhead overlaps the Adam pass."""
         if self.native:
             if self._frame is None:
-                self._frame = NativeFrame(self.model, cam.image_width, cam.image_height, self.lambda_dssim)
+                self._frame = NativeFrame(self.model, cam.image_width, cam.image_height, self.lambda_dssim, sync_free=self.sync_free)
             loss = self._frame.run(cam, gt, self.bg)
             from . import rasterizer as _r
             _r.last_num_rendered = self._frame.last_num_rendered

@@ -30,6 +30,11 @@
  * [upstream rasterize_points.cu: resizeFunctional]; the Python shim serves them from torch uint8 tensors
  * and keeps them alive for backward (ctx.save_for_backward in the stock shim).
  */
+/* Threading: the library keeps per-PROCESS state (tuning options, launch counter, kernel timers, the pinned word the
+ * synchronising forward reads N through).  Calls must come from one host thread at a time; concurrent calls from several
+ * threads -- or interleaving a forward on one stream with option changes -- are not supported (the stock extension has
+ * the same restriction: it launches on the legacy default stream and blocks on a cudaMemcpy).  Use one process per GPU,
+ * as bench.py / torchrun do.  Error strings (gms_last_error) are per thread. */
 #ifndef GMS_B200_H
 #define GMS_B200_H
 
@@ -87,10 +92,12 @@ typedef struct gms_raster_inputs {
 } gms_raster_inputs;
 
 /* Forward outputs (caller-allocated). */
+#define GMS_FORWARD_ONLY 1    /* flags bit 0: no backward will follow (inference / no_grad): skip the survivor lists */
 typedef struct gms_raster_outputs {
     float* out_color;     /* [3,H,W] */
     int32_t* radii;       /* [P] */
     float* out_invdepth;  /* [1,H,W] */
+    int32_t flags;        /* 0, or GMS_FORWARD_ONLY */
 } gms_raster_outputs;
 
 /* What forward hands back for backward: scratch base pointers (as returned by the callback) and N. */
@@ -101,7 +108,8 @@ typedef struct gms_raster_saved {
     int64_t num_rendered;   /* N = number of (tile, Gaussian) duplicates */
     int64_t num_visible;    /* Gaussians with radii > 0 (statistics; may be -1 if not computed) */
     int64_t binning_capacity; /* duplicates the binning region was sized for (== num_rendered on the synchronising call) */
-    int32_t flags;          /* bit 0: the binning region holds the point list only (counting binning, the default) */
+    int32_t flags;          /* bit 0: counting binning layout (point list first; no key arrays); bit 1: per-quad survivor lists
+                               of the forward compositing pass follow the point list (consumed by backward) */
 } gms_raster_saved;
 
 /* Gradients produced by backward (caller-allocated; NULL where the corresponding input was NULL). */
@@ -161,6 +169,9 @@ typedef struct gms_debug_views {
     const int32_t* ranges;       /* [T,2] */
     const float* final_T;        /* [H,W] */
     const int32_t* n_contrib;    /* [H,W] */
+    const float* dgeom;          /* [P,12] after a backward call: per-Gaussian sums the composite backward accumulated --
+                                    dL/dmean2D.xy (NDC-scaled), dL/dconic.xyz (stock half convention for xy), dL/d(conic_opacity.w),
+                                    dL/drgb.rgb, dL/dinvdepth, 2 unused -- i.e. the input of the preprocess backward */
 } gms_debug_views;
 int gms_debug_get_views(const gms_raster_saved* saved, int32_t P, int32_t W, int32_t H, gms_debug_views* views);
 /* The per-Gaussian preprocess results live in packed 48-byte records; this unpacks them into the stock

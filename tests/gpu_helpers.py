@@ -38,6 +38,11 @@ def run_gpu(S, inputs, dL_dcolor=None, dL_dinv=None, dev="cuda"):
         loss.backward()
         grads = {k: v.grad.detach().cpu().numpy() for k, v in t.items() if v.grad is not None}
         grads["means2D"] = m2d.grad.detach().cpu().numpy()
+        # what the composite backward handed to the preprocess backward (debug view of the per-Gaussian accumulators)
+        after = rasterizer.forward_debug_state(dbg["scratch"], dbg["num_rendered"], P, S.image_width, S.image_height, radii,
+                                               bin_state=dbg.get("bin_state"))
+        if "dgeom" in after:
+            grads["_dgeom"] = after["dgeom"].cpu().numpy()
     torch.cuda.synchronize()
     return color.detach().cpu().numpy(), radii.cpu().numpy(), invd.detach().cpu().numpy(), \
         {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in state.items()}, grads
@@ -69,23 +74,68 @@ def assert_forward_parity(st, color, radii, invd, state, tol=1e-5):
     np.testing.assert_array_equal(state["point_list"].astype(np.uint32), st.point_list)
     np.testing.assert_array_equal(state["tile_keys"].astype(np.uint64), st.keys_sorted >> np.uint64(32))
     np.testing.assert_array_equal(state["ranges"], st.ranges)
+    # Threshold-ambiguous pixels: the oracle flags a pixel when one of its skip / stop decisions (alpha < 1/255,
+    # T(1-alpha) < 1e-4) lies within the +-1e-6 relative band in which exp() (GPU: ex2.approx.ftz) may fall on the other side.
+    # They are REPORTED (count, worst error) and bounded by the largest change one flipped decision can cause: a splat
+    # blended at alpha = 1/255 with unit transmittance moves a channel by <= |c - behind| / 255 <= max colour / 255.
     ok = st.ambiguous == 0
-    assert ok.mean() > 0.999, f"too many threshold-ambiguous pixels: {1 - ok.mean():.2e}"
+    n_amb = int((~ok).sum())
+    err = np.abs(color - st.color)
+    err_ok = float(err[:, ok].max()) if ok.any() else 0.0
+    err_amb = float(err[:, ~ok].max()) if n_amb else 0.0
+    cmax = float(max(1.0, np.abs(st.rgb).max())) if st.radii.shape[0] else 1.0
+    print(f"[parity] {st.settings.image_width}x{st.settings.image_height} P={st.radii.shape[0]} N={st.N}: max|image-oracle| = {err_ok:.2e}; "
+          f"threshold-ambiguous pixels = {n_amb} ({n_amb / ok.size:.1e} of the image), worst there = {err_amb:.2e} (bound {cmax / 255:.1e})")
+    assert n_amb <= max(4, 5e-4 * ok.size), f"too many threshold-ambiguous pixels: {n_amb}"
     np.testing.assert_array_equal(state["n_contrib"][ok], st.n_contrib[ok])
-    assert np.abs(color - st.color)[:, ok].max() <= tol, np.abs(color - st.color)[:, ok].max()
+    assert err_ok <= tol, err_ok
     assert np.abs(invd - st.invdepth)[:, ok].max() <= tol
     assert np.abs(state["final_T"] - st.final_T)[ok].max() <= tol
-    if not ok.all():   # a flipped 1/255 or 1e-4 decision moves a pixel by at most one splat's contribution
-        assert np.abs(color - st.color)[:, ~ok].max() <= 2e-2
+    assert err_amb <= 2.0 * cmax / 255.0, err_amb
 
 
 # Gradients w.r.t. scales / rotations / cov3D go through the inverse of a nearly singular 2D covariance (flat mesh
-# Gaussians, s0 ~ 2e-8): the 1e-6 summation-order noise of the fp32 atomics in dL/dconic is amplified ~1e3x there (the
-# stock extension has the same non-determinism); the oracle sums in double.  Everything else stays at `tol`.
+# Gaussians, s0 ~ 2e-8): the summation-order noise of the fp32 atomics in dL/dconic is amplified by that Jacobian (the stock
+# extension has the same non-determinism; the oracle sums in double).  The backward pass is therefore checked in its TWO
+# LINEAR STAGES, each at a conditioning-independent tolerance (assert_backward_stages):
+#   (1) composite backward:  GPU per-Gaussian sums `dgeom`  vs  oracle composite_backward (double accumulation)
+#   (2) preprocess backward: GPU parameter gradients        vs  oracle preprocess_backward fed THE GPU's dgeom
+# (1) and (2) together imply the end-to-end gradient up to |J| * err(1); the end-to-end comparison below is kept as a sanity
+# check with the measured amplification as its slack.
 ILL_CONDITIONED = {"scales": 25.0, "rotations": 25.0, "cov3D_precomp": 25.0, "means3D": 2.5}
 
 
-def assert_grad_parity(g_gpu, g_ref, tol=2e-4):
+def assert_backward_stages(st, g_gpu, g_ref, tol_composite=2e-5, tol_pre=5e-5):
+    dg = g_gpu.get("_dgeom")
+    comp = g_ref.get("_composite")
+    if dg is None or comp is None:
+        return False
+    vis = st.radii > 0
+    groups = {"dL_dmean2D": dg[:, 0:2], "dL_dconic": dg[:, 2:5], "dL_dopacity": dg[:, 5], "dL_dcolor": dg[:, 6:9], "dL_dinvdepth": dg[:, 9]}
+    msg = []
+    for k, got in groups.items():
+        ref = np.asarray(comp[k], np.float64).reshape(got.shape)
+        scale = max(np.abs(ref).max(), 1e-30)
+        e = np.abs(got.astype(np.float64) - ref)[vis].max() / scale if vis.any() else 0.0
+        msg.append(f"{k} {e:.1e}")
+        assert e <= tol_composite, f"composite backward {k}: {e:.3e} > {tol_composite}"
+    # stage 2: the oracle's preprocess backward on the GPU's own sums
+    fed = dict(dL_dmean2D=dg[:, 0:2].astype(np.float64), dL_dconic=dg[:, 2:5].astype(np.float64), dL_dopacity=dg[:, 5].astype(np.float64),
+               dL_dcolor=dg[:, 6:9].astype(np.float64), dL_dinvdepth=dg[:, 9].astype(np.float64))
+    ref2 = raster.preprocess_backward(st, fed)
+    pairs = [("means3D", "dL_dmeans3D"), ("opacities", "dL_dopacity"), ("shs", "dL_dsh"), ("colors_precomp", "dL_dcolors_precomp"),
+             ("scales", "dL_dscales"), ("rotations", "dL_drotations"), ("cov3D_precomp", "dL_dcov3D")]
+    for kg, kr in pairs:
+        if kg in g_gpu and ref2.get(kr) is not None:
+            a, b = g_gpu[kg].astype(np.float64), np.asarray(ref2[kr], np.float64).reshape(g_gpu[kg].shape)
+            e = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+            msg.append(f"{kg} {e:.1e}")
+            assert e <= tol_pre, f"preprocess backward {kg}: {e:.3e} > {tol_pre}"
+    print("[parity] backward stages (max err / max|ref|): " + ", ".join(msg))
+    return True
+
+
+def assert_grad_parity(g_gpu, g_ref, tol=2e-4, st=None):
     pairs = [("means3D", "dL_dmeans3D"), ("means2D", "dL_dmeans2D"), ("opacities", "dL_dopacity"), ("shs", "dL_dsh"),
              ("colors_precomp", "dL_dcolors_precomp"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"),
              ("cov3D_precomp", "dL_dcov3D")]
@@ -99,3 +149,5 @@ def assert_grad_parity(g_gpu, g_ref, tol=2e-4):
             assert err <= lim, f"grad {kg}: max err / max |ref| = {err:.3e} > {lim}"
             checked += 1
     assert checked >= 5
+    if st is not None:
+        assert_backward_stages(st, g_gpu, g_ref)

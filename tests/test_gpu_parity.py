@@ -31,7 +31,7 @@ def test_forward_backward_parity_random_gaussians(P, W, H):
     color, radii, invd, state, grads = run_gpu(S, g, dC, dI)
     st, gref = run_oracle(S, g, dC, dI)
     assert_forward_parity(st, color, radii, invd, state)
-    assert_grad_parity(grads, gref)
+    assert_grad_parity(grads, gref, st=st)
 
 
 def test_ragged_image_size_not_multiple_of_16():
@@ -40,7 +40,7 @@ def test_ragged_image_size_not_multiple_of_16():
     color, radii, invd, state, grads = run_gpu(S, g, dC, dI)
     st, gref = run_oracle(S, g, dC, dI)
     assert_forward_parity(st, color, radii, invd, state)
-    assert_grad_parity(grads, gref)
+    assert_grad_parity(grads, gref, st=st)
 
 
 @pytest.mark.parametrize("aa", [False, True])
@@ -50,7 +50,7 @@ def test_antialiasing_and_scale_modifier(aa):
     color, radii, invd, state, grads = run_gpu(S, g, dC, dI)
     st, gref = run_oracle(S, g, dC, dI)
     assert_forward_parity(st, color, radii, invd, state)
-    assert_grad_parity(grads, gref)
+    assert_grad_parity(grads, gref, st=st)
 
 
 @pytest.mark.parametrize("deg", [0, 1, 2, 3])
@@ -60,7 +60,7 @@ def test_sh_degrees(deg):
     color, radii, invd, state, grads = run_gpu(S, g, dC, dI)
     st, gref = run_oracle(S, g, dC, dI)
     assert_forward_parity(st, color, radii, invd, state)
-    assert_grad_parity(grads, gref)
+    assert_grad_parity(grads, gref, st=st)
 
 
 def test_precomputed_colors_and_covariance():
@@ -74,7 +74,7 @@ def test_precomputed_colors_and_covariance():
     color, radii, invd, state, grads = run_gpu(S, g2, dC, dI)
     st, gref = run_oracle(S, g2, dC, dI)
     assert_forward_parity(st, color, radii, invd, state)
-    assert_grad_parity(grads, gref)
+    assert_grad_parity(grads, gref, st=st)
 
 
 def test_saturating_scene_early_termination_and_long_lists():
@@ -104,54 +104,44 @@ def test_flat_mesh_gaussians_edge_on_slivers():
     assert_grad_parity(grads, gref, tol=5e-4)
 
 
-def test_quad_masks_do_not_change_results():
-    S, g = _case(8000, 320, 240, seed=9)
-    dC, dI = _grads_in(240, 320, 8)
-    a = run_gpu(S, g, dC, dI)
-    old, oldv = _lib.set_option("quad_masks", 0), _lib.set_option("composite_version", 1)
-    try:
-        b = run_gpu(S, g, dC, dI)
-    finally:
-        _lib.set_option("quad_masks", old); _lib.set_option("composite_version", oldv)
-    np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[2], b[2])
-    np.testing.assert_array_equal(a[3]["n_contrib"], b[3]["n_contrib"])
-    for k in a[4]:
-        sc = np.abs(b[4][k]).max() + 1e-20
-        assert np.abs(a[4][k] - b[4][k]).max() / sc < (5e-3 if k in ('scales', 'rotations') else 2e-4), k   # float atomics: summation order differs
-
-
-@pytest.mark.parametrize("version,tile_order", [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (4, 0), (4, 1)])
-def test_composite_generations_agree_and_match_oracle(version, tile_order):
-    """Generation 1 (block-synchronous) and 2 (warp-independent, longest-first tile order) are the same function."""
+@pytest.mark.parametrize("fwd,bwd,tile_order,minb", [(2, 5, 1, 6), (2, 5, 0, 4), (2, 5, 1, 8), (2, 3, 1, 6), (3, 3, 0, 6), (3, 5, 1, 6)])
+@pytest.mark.parametrize("with_depth", [True, False])
+def test_composite_kernel_variants_agree_and_match_oracle(fwd, bwd, tile_order, minb, with_depth):
+    """Forward: scalar (2, writes the per-quad survivor lists) / packed f32x2 (3).  Backward: survivor-list driven (5,
+    default) / predecessor that re-derives the survivors (3; also what runs after a forward without lists, e.g. fwd=3).
+    Both DEPTH template variants, every launch-bounds variant, with and without the longest-first tile order."""
     S, g = _case(12000, 352, 272, seed=21, extent=1.0, scale_mu=-2.2)
     dC, dI = _grads_in(272, 352, 9)
-    old_v, old_o = _lib.set_option("composite_version", version), _lib.set_option("tile_order", tile_order)
-    try:
-        color, radii, invd, state, grads = run_gpu(S, g, dC, dI)
-    finally:
-        _lib.set_option("composite_version", old_v); _lib.set_option("tile_order", old_o)
-    st, gref = run_oracle(S, g, dC, dI)
-    assert_forward_parity(st, color, radii, invd, state)
-    assert_grad_parity(grads, gref)
-
-
-@pytest.mark.parametrize("reduce", [1, 0])
-@pytest.mark.parametrize("with_depth", [True, False])
-@pytest.mark.parametrize("P,W,H", [(20000, 400, 300), (3000, 333, 201)])
-def test_backward_warp_reduction_variants(P, W, H, with_depth, reduce):
-    """Option "bwd_reduce": 1 (default) -- k_composite_bwd3 parks the per-lane moment sums of up to three splats in a
-    shared-memory panel and reduces rows; 0 -- 12-shuffle transpose-fold per splat.  Both template variants (with /
-    without the inverse-depth channel), full and partial panels, ragged image."""
-    S, g = _case(P, W, H, seed=P + 1)
-    dC, dI = _grads_in(H, W, 5)
-    old = _lib.set_option("bwd_reduce", reduce)
+    olds = [_lib.set_option(k, v) for k, v in (("composite_fwd", fwd), ("composite_bwd", bwd), ("tile_order", tile_order), ("bwd_minblocks", minb))]
     try:
         color, radii, invd, state, grads = run_gpu(S, g, dC, dI if with_depth else None)
     finally:
-        _lib.set_option("bwd_reduce", old)
+        for k, v in zip(("composite_fwd", "composite_bwd", "tile_order", "bwd_minblocks"), olds):
+            _lib.set_option(k, v)
     st, gref = run_oracle(S, g, dC, dI if with_depth else None)
     assert_forward_parity(st, color, radii, invd, state)
-    assert_grad_parity(grads, gref)
+    assert_grad_parity(grads, gref, st=st)
+
+
+@pytest.mark.parametrize("P,W,H,scale_mu", [(20000, 400, 300, -2.6), (3000, 333, 201, -2.6), (600, 640, 400, -0.8), (40000, 96, 64, -2.0)])
+def test_survivor_list_backward_edge_cases(P, W, H, scale_mu):
+    """Survivor-driven backward on: partial panels and ragged images, huge splats (lists of one entry per quad for most
+    tiles), and a small saturated image (long lists cut short by early termination: the lists end where the forward stopped)."""
+    S, g = _case(P, W, H, seed=P + 1, scale_mu=scale_mu)
+    dC, dI = _grads_in(H, W, 5)
+    color, radii, invd, state, grads = run_gpu(S, g, dC, dI)
+    st, gref = run_oracle(S, g, dC, dI)
+    assert_forward_parity(st, color, radii, invd, state)
+    assert_grad_parity(grads, gref, st=st)
+    # a second backward through the predecessor kernel gives the same gradients up to the atomics' summation order
+    old = _lib.set_option("composite_bwd", 3)
+    try:
+        grads3 = run_gpu(S, g, dC, dI)[4]
+    finally:
+        _lib.set_option("composite_bwd", old)
+    for k in grads:
+        sc = np.abs(grads3[k]).max() + 1e-20
+        assert np.abs(grads[k] - grads3[k]).max() / sc < (5e-3 if k in ("scales", "rotations") else 2e-4), k
 
 
 @pytest.mark.parametrize("impl", [0, 1])

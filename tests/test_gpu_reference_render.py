@@ -92,8 +92,9 @@ def _oracle_chain(p, S, dC, gpu, triangles=None):
     assert float(((gs - sc.detach()).abs() / sc.detach()).max()) <= 1e-5
     st = raster.forward(S, gx, op.detach(), shs=fe.contiguous(), scales=gs, rotations=gr)
     g = raster.backward(st, dC)
-    torch.autograd.backward([xyz, sc, rot, op], [torch.tensor(g["dL_dmeans3D"]), torch.tensor(g["dL_dscales"]),
-                                                  torch.tensor(g["dL_drotations"]), torch.tensor(g["dL_dopacity"])])
+    outs = [(xyz, g["dL_dmeans3D"]), (sc, g["dL_dscales"]), (rot, g["dL_drotations"]), (op, g["dL_dopacity"])]
+    outs = [(t, torch.tensor(gr).reshape(t.shape)) for t, gr in outs if t.requires_grad]     # animated path: rotation is a constant of the triangles
+    torch.autograd.backward([t for t, _ in outs], [gr for _, gr in outs])
     grads = dict(vertices=tv.grad, _alpha=ta.grad, _scale=ts.grad, _opacity=top.grad,
                  _features_dc=torch.tensor(g["dL_dsh"][:, :1]), _features_rest=torch.tensor(g["dL_dsh"][:, 1:]))
     return st, grads

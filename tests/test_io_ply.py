@@ -55,3 +55,27 @@ def test_mesh_model_params_round_trip(tmp_path):
     q = io_ply.load_mesh_model(ply)
     for k in ("vertices", "faces", "_alpha", "_scale", "_features_dc", "_features_rest", "_opacity"):
         assert torch.equal(getattr(p, k), getattr(q, k)), k
+
+
+def test_reads_a_checkpoint_written_by_the_reference(golden_dir):
+    """tests/golden/ply/ was written by the reference's own GaussianMeshModel.save_ply (tests/golden/make_ply_golden.py):
+    property order, channel-major SH layout and the model_params.pt keys are the reference's, not this repo's writer's."""
+    ply = os.path.join(golden_dir, "ply", "point_cloud.ply")
+    want = np.load(os.path.join(golden_dir, "ply", "expected.npz"))
+    g = io_ply.load_gaussian_ply(ply)
+    for k in ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation"):
+        np.testing.assert_array_equal(g[k].numpy(), want[k])
+    p = io_ply.load_mesh_model(ply)
+    for k in ("vertices", "faces", "_alpha", "_scale", "_opacity", "_features_dc", "_features_rest"):
+        np.testing.assert_array_equal(getattr(p, k).numpy(), want[k])
+    assert p.faces.dtype == torch.int64
+
+
+def test_two_column_scaling_gets_the_s0_column_like_the_reference(tmp_path):
+    xyz, fdc, frest, op, sc, rot = _random_model(P=11, S=2)
+    p = str(tmp_path / "point_cloud.ply")
+    io_ply.save_gaussian_ply(p, xyz, fdc, frest, op, sc, rot)
+    data, names = io_ply.read_ply_vertices(p)
+    assert [n for n in names if n.startswith("scale_")] == ["scale_0", "scale_1", "scale_2"]       # scene/gaussian_model.py:179-180
+    np.testing.assert_allclose(np.asarray(data["scale_0"]), np.log(np.float32(1e-8)), rtol=1e-6)
+    np.testing.assert_array_equal(np.asarray(data["scale_2"]), sc[:, 1].numpy())

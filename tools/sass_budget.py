@@ -35,7 +35,7 @@ def kernels(patterns):
 
 
 def main():
-    pats = sys.argv[1:] or ["k_composite_bwd3ILi6ELb0", "k_composite_fwd2"]
+    pats = sys.argv[1:] or ["k_composite_bwd5ILi6ELb0", "k_composite_bwd3ILi6ELb0", "k_composite_fwd2ILb1"]
     for name, body in kernels(pats):
         print(f"== {name}: {len(body)} SASS instructions")
         addr_index = {a: i for i, (a, _) in enumerate(body)}
