@@ -603,8 +603,12 @@ def main():
     gts_host_f32 = [g.cpu().pin_memory() for g in gts]
     cam_host = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center.reshape(-1)]).pin_memory()
                 for c in cams]
+    loss_fn = None
+    if args.reference_ops:
+        import aten_reference           # tests/: the ATen restatement of utils/loss_utils.py
+        loss_fn = aten_reference.training_loss
     trainer = MeshTrainer(model, bg, world=world, rank=rank, optimizer_step=not args.no_optimizer, fast=not args.reference_ops,
-                          native=not (args.no_native or args.reference_ops), sync_free=not args.sync_frame)
+                          native=not (args.no_native or args.reference_ops), sync_free=not args.sync_frame, loss_fn=loss_fn)
 
     def barrier():
         if world > 1:

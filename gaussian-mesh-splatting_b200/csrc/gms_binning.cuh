@@ -7,24 +7,20 @@
 // (one stable 32-bit sort over P, gms_kernels.cu), the per-tile lists are a STABLE COUNTING SORT of the duplicates by
 // tile id -- no keys have to be materialised and nothing has to be sorted again:
 //
-//   phase 1  every warp owns a contiguous slice of the depth order and counts, per tile, how many of its Gaussians cover
-//            it (16-bit counters in the warp's own shared-memory row, two tiles per 32-bit word);  a CTA-level
-//            exclusive scan over the warps' rows turns them into warp offsets and yields the CTA's per-tile count
-//            M[cta][tile]                                                                                  -> grid.sync
-//   phase 2a per tile, exclusive scan of M[.][tile] over the CTAs (in place) and total[tile]              -> grid.sync
+//   phase 1  every CTA owns a contiguous slice of the depth order and counts, per tile, how many of its Gaussians cover it
+//            (one row of counters in shared memory, order-free: each lane walks its own rectangle)  -> M[cta][tile]  -> grid.sync
+//   phase 2a per tile, exclusive scan of M[.][tile] over the CTAs (in place) and total[tile]                    -> grid.sync
 //   phase 2b every CTA scans total[] (block scan in shared memory) into tile starts; base[tile] = start + M[cta][tile]
 //            stays in shared memory; CTA 0 writes ranges[] and N.  N > capacity: overflow flag, empty ranges, no writes.
-//   phase 3  every warp walks its slice again IN ORDER and writes
-//            point_list[base[tile] + row[warp][tile]++] = Gaussian id.
-// Both walks are DENSE over (Gaussian, tile) pairs: a batch of 32 Gaussians is loaded one per lane (ids and rectangles
-// two / one batch ahead), a warp scan of the rectangle areas numbers the batch's pairs Gaussian-major, and every step hands
-// 32 consecutive pairs to the 32 lanes (owner found by a 5-step shuffle search) -- full lanes whatever the rectangle sizes.
-// In phase 3 the lanes of a step that hit the same tile (different Gaussians, lane order = depth order) are ranked with
-// match.any and served by ONE shared-memory atomic; steps follow each other in program order, so slots come out in depth order.
+//   phase 3  the CTA walks its slice again, a batch of 32 Gaussians per warp, and writes
+//            point_list[base[tile] + row[tile]++] = Gaussian id  with the batches COMMITTING IN DEPTH ORDER: a warp
+//            prepares its batch on its own (loads two batches ahead, a warp scan numbers the batch's (Gaussian, tile) pairs
+//            Gaussian-major, every step hands 32 consecutive pairs to the 32 lanes, lanes of a step that hit the same tile
+//            are ranked with match.any), then waits for its turn and draws the slots with one shared-memory atomic per
+//            distinct tile and step.  Only those atomics are serialised; 2 CTAs x 16 warps per SM keep the rest overlapped.
 //
 // The result is bit-identical to the stock (tile << 32 | depth) sort (tests/test_gpu_parity.py).  Device-side N, no host
-// synchronisation, no scan over P, no key arrays: at 1M Gaussians / 1080p it replaces 0.016 (scan) + 0.04 (emit) + 0.125
-// (sort, cub) + 0.016 (ranges) ms.  The grid is one CTA per SM (cooperative launch, grid.sync between the phases).
+// synchronisation, no scan over P, no key arrays.  Grid = 2 CTAs per SM (cooperative launch, grid.sync between the phases).
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -47,17 +43,11 @@ struct GmsBinArgs {
     volatile uint32_t* n_host;  // mapped pinned host [2] or NULL: N, overflow flag (readable without a sync once the kernel ran)
 };
 
-// shared memory: W rows of T 16-bit counters (as ceil(T/2) words) + T 32-bit bases
-static inline size_t gms_bin_smem_bytes(int T, int warps) {
-    const size_t words = (size_t)(T + 1) / 2;
-    return (words * warps + (size_t)T) * sizeof(uint32_t) + 64;
-}
-// largest warp count (power of two, <= 16) whose rows fit next to the bases in `budget` bytes; 0: does not fit at all
-static inline int gms_bin_warps(int T, size_t budget) {
-    for (int w = 16; w >= 2; w >>= 1)
-        if (gms_bin_smem_bytes(T, w) <= budget) return w;
-    return 0;
-}
+constexpr int GMS_BIN_THREADS = 512;        // 16 warps per CTA
+constexpr int GMS_BIN_STEPS = 8;            // steps (of 32 pairs) prepared ahead of the ordered section
+
+// dynamic shared memory: one row of T 32-bit counters + T 32-bit bases
+static inline size_t gms_bin_smem_bytes(int T) { return 2 * (size_t)T * sizeof(uint32_t) + 64; }
 
 __device__ __forceinline__ void gms_bin_unpack(const uint2 r, int gx, int& t00, int& w, int& nt) {
     const int x0 = (int)(r.x & 0xffffu), y0 = (int)(r.x >> 16);
@@ -67,98 +57,69 @@ __device__ __forceinline__ void gms_bin_unpack(const uint2 r, int gx, int& t00, 
     if (nt <= 0) { nt = 0; w = 1; }
 }
 
-// One pass over the warp's slice [j_lo, j_hi) of the depth order, 32 (Gaussian, tile) pairs per step.
-// PLACE = false: count into `row`.  PLACE = true: ordered slots from `row`, ids to point_list.
-template <bool PLACE>
-__device__ __forceinline__ void gms_bin_walk(const GmsBinArgs& a, uint32_t j_lo, uint32_t j_hi, int lane, uint32_t* row, const uint32_t* base) {
+__global__ void __launch_bounds__(GMS_BIN_THREADS, 2) k_bin_tiles(GmsBinArgs a) {
+    extern __shared__ uint32_t bin_smem[];
+    __shared__ uint32_t s_part[GMS_BIN_THREADS];
+    __shared__ uint32_t s_grp[GMS_BIN_THREADS / 32][64];
+    __shared__ uint32_t s_n;
+    __shared__ volatile uint32_t s_turn;
+    cg::grid_group grid = cg::this_grid();
+    constexpr int W = GMS_BIN_THREADS / 32;
     const unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
-    // software pipeline: ids two batches ahead, rectangles one batch ahead
-    uint32_t g_cur = 0, g_nx = 0;
-    uint2 r_cur = make_uint2(0u, 0u);
-    if (j_lo + lane < j_hi) { g_cur = a.order[j_lo + lane]; r_cur = a.rect[g_cur]; }
-    if (j_lo + 32 + lane < j_hi) g_nx = a.order[j_lo + 32 + lane];
-    for (uint32_t j0 = j_lo; j0 < j_hi; j0 += 32) {
-        const uint32_t g = g_cur;
-        int t00, w, nt;
-        gms_bin_unpack((j0 + lane < j_hi) ? r_cur : make_uint2(0u, 0u), a.gx, t00, w, nt);
-        // prefetch
-        g_cur = g_nx;
-        r_cur = (j0 + 32 + lane < j_hi) ? a.rect[g_cur] : make_uint2(0u, 0u);
-        g_nx = (j0 + 64 + lane < j_hi) ? a.order[j0 + 64 + lane] : 0u;
-        // number the batch's pairs Gaussian-major
-        int inc = nt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += y; }
-        const int tot = __shfl_sync(FULL, inc, 31);
-        const int exc = inc - nt;
-        for (int p0 = 0; p0 < tot; p0 += 32) {
-            const int p = p0 + lane;
-            const bool active = p < tot;
-            int lo = 0;         // owner = first lane whose inclusive prefix exceeds p
-#pragma unroll
-            for (int st = 16; st >= 1; st >>= 1) { const int v = __shfl_sync(FULL, inc, lo + st - 1); if (v <= p) lo += st; }
-            const int owner = lo & 31;
-            const int k = p - __shfl_sync(FULL, exc, owner);
-            const int t0s = __shfl_sync(FULL, t00, owner), ws = __shfl_sync(FULL, w, owner);
-            const int yy = (int)(((float)k + 0.5f) * __frcp_rn((float)ws));      // exact floor(k / ws) for k < 2^20
-            const int t = t0s + yy * a.gx + (k - yy * ws);
-            const int sh = (t & 1) * 16;
-            if (!PLACE) {
-                if (active) atomicAdd(&row[t >> 1], 1u << sh);
-            } else {
-                const uint32_t gs = __shfl_sync(FULL, g, owner);
-                const uint32_t peers = __match_any_sync(FULL, active ? (uint32_t)t : (0x40000000u | (uint32_t)lane));
-                const int leader = __ffs(peers) - 1;
-                uint32_t old = 0;
-                if (active && lane == leader) old = atomicAdd(&row[t >> 1], (uint32_t)__popc(peers) << sh);
-                old = __shfl_sync(FULL, old, leader);
-                if (active) {
-                    const uint32_t pos = base[t] + ((old >> sh) & 0xffffu) + (uint32_t)__popc(peers & lt);
-                    a.point_list[pos] = gs;
-                    if (a.tile_keys) a.tile_keys[pos] = (uint32_t)t;
+    const int T = a.T, G = (int)gridDim.x;
+    uint32_t* row = bin_smem;               // [T] this CTA's running count per tile
+    uint32_t* base = bin_smem + T;          // [T] first list position of this CTA's entries per tile
+    for (int i = threadIdx.x; i < T; i += GMS_BIN_THREADS) row[i] = 0;
+    if (threadIdx.x == 0) s_turn = 0;
+    // slice of the depth order owned by this CTA, in batches of 32 Gaussians dealt round-robin to the warps
+    const uint32_t nvis = min(*a.nvis, (uint32_t)a.P);
+    const uint32_t per = ((nvis + G - 1) / G + 31u) & ~31u;
+    const uint32_t j_lo = min((uint32_t)blockIdx.x * per, nvis), j_hi = min(j_lo + per, nvis);
+    const uint32_t nbatch = (j_hi - j_lo + 31u) / 32u;
+    __syncthreads();
+
+    // ---- phase 1: counting (order-free): lane = Gaussian, each lane walks its own rectangle
+    {
+        uint32_t b = warp;
+        uint32_t g_nx = 0; uint2 r_cur = make_uint2(0u, 0u);
+        if (b < nbatch) { const uint32_t j = j_lo + 32u * b + lane; if (j < j_hi) r_cur = a.rect[a.order[j]]; }
+        if (b + W < nbatch) { const uint32_t j = j_lo + 32u * (b + W) + lane; if (j < j_hi) g_nx = a.order[j]; }
+        for (; b < nbatch; b += W) {
+            int t00, w, nt;
+            gms_bin_unpack(r_cur, a.gx, t00, w, nt);
+            {   // prefetch: rectangle of the next batch of this warp, id of the one after
+                const uint32_t j1 = j_lo + 32u * (b + W) + lane, j2 = j_lo + 32u * (b + 2 * W) + lane;
+                r_cur = (b + W < nbatch && j1 < j_hi) ? a.rect[g_nx] : make_uint2(0u, 0u);
+                g_nx = (b + 2 * W < nbatch && j2 < j_hi) ? a.order[j2] : 0u;
+            }
+            const bool big = nt >= 64;
+            if (!big) {
+                int t = t00, x = 0;
+                for (int k = 0; k < nt; k++) {
+                    atomicAdd(&row[t], 1u);
+                    if (++x == w) { x = 0; t += a.gx - w + 1; } else t++;
                 }
+            }
+            uint32_t m = __ballot_sync(FULL, big);
+            while (m) {     // large rectangles: the warp shares one
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int t0s = __shfl_sync(FULL, t00, src), ws = __shfl_sync(FULL, w, src), nts = __shfl_sync(FULL, nt, src);
+                for (int k = lane; k < nts; k += 32) { const int yy = k / ws; atomicAdd(&row[t0s + yy * a.gx + (k - yy * ws)], 1u); }
             }
         }
     }
-}
-
-__global__ void __launch_bounds__(512, 1) k_bin_tiles(GmsBinArgs a) {
-    extern __shared__ uint32_t bin_smem[];
-    __shared__ uint32_t s_part[512];
-    __shared__ uint32_t s_grp[16][64];
-    __shared__ uint32_t s_n;
-    cg::grid_group grid = cg::this_grid();
-    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T = a.T, words = (T + 1) >> 1, G = (int)gridDim.x;
-    uint32_t* rows = bin_smem;                          // [W][words]
-    uint32_t* base = bin_smem + (size_t)W * words;      // [T]
-    uint32_t* row = rows + (size_t)warp * words;
-    for (int i = threadIdx.x; i < W * words; i += blockDim.x) rows[i] = 0;
-    // slice of the depth order owned by this warp
-    const uint32_t nvis = min(*a.nvis, (uint32_t)a.P);
-    const uint32_t nwarps = gridDim.x * W, gw = blockIdx.x * W + warp;
-    const uint32_t per = (nvis + nwarps - 1) / nwarps;
-    const uint32_t j_lo = min(gw * per, nvis), j_hi = min(j_lo + per, nvis);
     __syncthreads();
-
-    // ---- phase 1: counting
-    gms_bin_walk<false>(a, j_lo, j_hi, lane, row, nullptr);
-    __syncthreads();
-    // warps' rows -> exclusive offsets inside the CTA; CTA count per tile -> M
-    {
+    {   // CTA count per tile -> M; the row restarts from 0 and becomes the running count of phase 3
         uint32_t* Mrow = a.M + (size_t)blockIdx.x * T;
-        for (int i = threadIdx.x; i < words; i += blockDim.x) {
-            uint32_t run = 0;   // two 16-bit lanes at once; a CTA's count of one tile stays below 65536 (host checks P / grid)
-            for (int wq = 0; wq < W; wq++) { const uint32_t c = rows[(size_t)wq * words + i]; rows[(size_t)wq * words + i] = run; run += c; }
-            if (2 * i + 1 < T) *reinterpret_cast<uint2*>(Mrow + 2 * i) = make_uint2(run & 0xffffu, run >> 16);
-            else Mrow[2 * i] = run & 0xffffu;
-        }
+        for (int i = threadIdx.x; i < T; i += GMS_BIN_THREADS) { Mrow[i] = row[i]; row[i] = 0; }
     }
     grid.sync();
 
-    // ---- phase 2a: per tile, exclusive scan over the CTAs.  64 adjacent tiles per CTA (two per lane: coalesced rows of M);
-    // the W warps split the CTA axis, combine their partial sums through shared memory, then write the offsets.
+    // ---- phase 2a: per tile, exclusive scan over the CTAs.  64 adjacent tiles per CTA round (two per lane: coalesced rows
+    // of M); the W warps split the CTA axis, combine their partial sums through shared memory, then write the offsets.
     {
         const int cper = (G + W - 1) / W;
         const int c_lo = min(warp * cper, G), c_hi = min(c_lo + cper, G);
@@ -206,23 +167,23 @@ __global__ void __launch_bounds__(512, 1) k_bin_tiles(GmsBinArgs a) {
 
     // ---- phase 2b: tile starts (every CTA, redundantly, in shared memory); base[] = start + this CTA's offset
     {
-        for (int i = threadIdx.x; i < T; i += blockDim.x) base[i] = a.total[i];
+        for (int i = threadIdx.x; i < T; i += GMS_BIN_THREADS) base[i] = a.total[i];
         __syncthreads();
-        const int per_t = (T + blockDim.x - 1) / blockDim.x;
+        const int per_t = (T + GMS_BIN_THREADS - 1) / GMS_BIN_THREADS;
         const int t0 = min((int)threadIdx.x * per_t, T), t1 = min(t0 + per_t, T);
-        uint32_t s = 0;
-        for (int t = t0; t < t1; t++) s += base[t];
-        s_part[threadIdx.x] = s;
+        uint32_t sum = 0;
+        for (int t = t0; t < t1; t++) sum += base[t];
+        s_part[threadIdx.x] = sum;
         __syncthreads();
-        if (warp == 0) {        // exclusive scan of <= 512 partials by one warp
+        if (warp == 0) {        // exclusive scan of the partials by one warp
             uint32_t carry = 0;
-            for (int c0 = 0; c0 < (int)blockDim.x; c0 += 32) {
+            for (int c0 = 0; c0 < GMS_BIN_THREADS; c0 += 32) {
                 const uint32_t v = s_part[c0 + lane];
                 uint32_t x = v;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
                 s_part[c0 + lane] = carry + x - v;
-                carry += __shfl_sync(0xffffffffu, x, 31);
+                carry += __shfl_sync(FULL, x, 31);
             }
             if (lane == 0) s_n = carry;
         }
@@ -233,7 +194,7 @@ __global__ void __launch_bounds__(512, 1) k_bin_tiles(GmsBinArgs a) {
         for (int t = t0; t < t1; t++) {
             const uint32_t tot = base[t];
             base[t] = run;
-            if (blockIdx.x == 0) a.ranges[t] = overflow ? make_int2(0, 0) : make_int2((int)run, (int)(run + tot));
+            if (blockIdx.x == 0) a.ranges[t] = (overflow || tot == 0) ? make_int2(0, 0) : make_int2((int)run, (int)(run + tot));   // untouched tiles stay (0, 0) like the stock's
             run += tot;
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -243,10 +204,80 @@ __global__ void __launch_bounds__(512, 1) k_bin_tiles(GmsBinArgs a) {
         if (overflow) return;       // uniform over the grid: no further grid.sync follows
         __syncthreads();
         const uint32_t* Mrow = a.M + (size_t)blockIdx.x * T;
-        for (int i = threadIdx.x; i < T; i += blockDim.x) base[i] += Mrow[i];
+        for (int i = threadIdx.x; i < T; i += GMS_BIN_THREADS) base[i] += Mrow[i];
         __syncthreads();
     }
 
-    // ---- phase 3: ordered placement
-    gms_bin_walk<true>(a, j_lo, j_hi, lane, row, base);
+    // ---- phase 3: ordered placement.  Each warp prepares its batch (32 Gaussians -> their (Gaussian, tile) pairs numbered
+    // Gaussian-major, 32 consecutive pairs per step; lanes of a step that hit the same tile are ranked with match.any), then
+    // takes its TURN -- batches commit in depth order -- to draw the slots from the CTA's row with one shared-memory atomic
+    // per distinct tile and step.  Only the atomics are serialised; loads, pair numbering and the stores overlap across warps.
+    {
+        uint32_t b = warp;
+        uint32_t g_cur = 0, g_nx = 0; uint2 r_cur = make_uint2(0u, 0u);
+        if (b < nbatch) { const uint32_t j = j_lo + 32u * b + lane; if (j < j_hi) { g_cur = a.order[j]; r_cur = a.rect[g_cur]; } }
+        if (b + W < nbatch) { const uint32_t j = j_lo + 32u * (b + W) + lane; if (j < j_hi) g_nx = a.order[j]; }
+        for (; b < nbatch; b += W) {
+            const uint32_t g = g_cur;
+            int t00, w, nt;
+            gms_bin_unpack(r_cur, a.gx, t00, w, nt);
+            {
+                const uint32_t j1 = j_lo + 32u * (b + W) + lane, j2 = j_lo + 32u * (b + 2 * W) + lane;
+                g_cur = g_nx;
+                r_cur = (b + W < nbatch && j1 < j_hi) ? a.rect[g_cur] : make_uint2(0u, 0u);
+                g_nx = (b + 2 * W < nbatch && j2 < j_hi) ? a.order[j2] : 0u;
+            }
+            int inc = nt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += y; }
+            const int tot = __shfl_sync(FULL, inc, 31);
+            const int exc = inc - nt;
+            const float rw = __fdividef(1.0f, (float)w);
+            bool mine = false;      // this warp holds the turn
+            for (int p0 = 0; p0 < tot || !mine; p0 += 32 * GMS_BIN_STEPS) {
+                int tt[GMS_BIN_STEPS]; uint32_t gg[GMS_BIN_STEPS], meta[GMS_BIN_STEPS];
+#pragma unroll
+                for (int s = 0; s < GMS_BIN_STEPS; s++) {
+                    tt[s] = -1; gg[s] = 0; meta[s] = 0;
+                    if (p0 + 32 * s >= tot) continue;       // (uniform) nothing beyond this step
+                    const int p = p0 + 32 * s + lane;
+                    const bool active = p < tot;
+                    int lo = 0;         // owner = first lane whose inclusive prefix exceeds p
+#pragma unroll
+                    for (int st = 16; st >= 1; st >>= 1) { const int v = __shfl_sync(FULL, inc, lo + st - 1); if (v <= p) lo += st; }
+                    const int owner = lo & 31;
+                    const int k = p - __shfl_sync(FULL, exc, owner);
+                    const int t0s = __shfl_sync(FULL, t00, owner), ws = __shfl_sync(FULL, w, owner);
+                    const float rws = __shfl_sync(FULL, rw, owner);
+                    gg[s] = __shfl_sync(FULL, g, owner);
+                    const int yy = (int)(((float)k + 0.5f) * rws);          // floor(k / ws): exact for k < 2^20 (error of the approximate reciprocal << 0.5 / ws)
+                    const int t = t0s + yy * a.gx + (k - yy * ws);
+                    tt[s] = active ? t : -1;
+                    const uint32_t peers = __match_any_sync(FULL, active ? (uint32_t)t : (0x40000000u | (uint32_t)lane));
+                    meta[s] = (uint32_t)(__ffs(peers) - 1) | ((uint32_t)__popc(peers & lt) << 8) | ((uint32_t)__popc(peers) << 16);
+                }
+                if (!mine) {
+                    while (s_turn != b) __nanosleep(32);
+                    __syncwarp();
+                    mine = true;
+                }
+#pragma unroll
+                for (int s = 0; s < GMS_BIN_STEPS; s++) {
+                    if (p0 + 32 * s >= tot) break;          // uniform
+                    const int leader = (int)(meta[s] & 0xffu);
+                    uint32_t old = 0;
+                    if (tt[s] >= 0 && lane == leader) old = atomicAdd(&row[tt[s]], meta[s] >> 16);
+                    old = __shfl_sync(FULL, old, leader);
+                    if (tt[s] >= 0) {
+                        const uint32_t pos = base[tt[s]] + old + ((meta[s] >> 8) & 0xffu);
+                        a.point_list[pos] = gg[s];
+                        if (a.tile_keys) a.tile_keys[pos] = (uint32_t)tt[s];
+                    }
+                }
+                if (p0 + 32 * GMS_BIN_STEPS >= tot) break;
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); s_turn = b + 1; }
+        }
+    }
 }

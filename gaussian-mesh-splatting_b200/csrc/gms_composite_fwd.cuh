@@ -2,8 +2,8 @@
 //
 // k_composite_fwd2<EMIT>  default.  Scalar fp32, two pixels per lane.  EMIT: while compositing, every warp appends the list
 //                         positions of the splats that actually BLENDED into at least one of its 64 pixels to a per-quad
-//                         SURVIVOR LIST (ballot-free: one vote per visited splat, one coalesced 128-byte store per 32
-//                         survivors).  The backward pass then walks exactly those pairs (gms_composite_bwd.cuh):
+//                         SURVIVOR LIST (a bit per visited splat in a lane-local mask, ONE warp OR-reduction per
+//                         round, the set lanes store their positions compacted).  The backward pass then walks exactly those pairs (gms_composite_bwd.cuh):
 //                         at 1M / 1080p 3.7 M of the 18.4 M (quad, splat) pairs, with no culling test and 1/5 of the rounds.
 // k_composite_fwd3        A/B alternative: the same arithmetic as packed fp32x2 vectors (bit-identical result, slower:
 //                         the forward is FMA/ALU-pipe bound and packing adds staging cost).
@@ -32,7 +32,7 @@ k_composite_fwd2(const int2* __restrict__ ranges, const int* __restrict__ tile_o
     bool live0 = g.in0, live1 = g.in1;
     // survivor list of this quad: region [4 * rng.x + warp * n, + n) of `surv`, positions relative to the tile's list
     uint32_t* const qlist = EMIT ? surv + 4 * (size_t)rng.x + (size_t)warp * n : nullptr;
-    uint32_t scount = 0, spend = 0;
+    uint32_t scount = 0;
 
     int id_cur = (lane < n) ? (int)point_list[rng.x + lane] : -1;
     float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
@@ -56,6 +56,7 @@ k_composite_fwd2(const int2* __restrict__ ranges, const int* __restrict__ tile_o
             id_nx = (k < n) ? (int)point_list[rng.x + k] : -1;
         }
         __syncwarp();
+        uint32_t blended = 0;       // EMIT: bit j = splat j of this round blended into one of this lane's pixels
         while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1;
@@ -98,19 +99,17 @@ k_composite_fwd2(const int2* __restrict__ ranges, const int* __restrict__ tile_o
                 }
                 b1 = ok;
             }
-            if (EMIT && __any_sync(0xffffffffu, b0 || b1)) {        // this (quad, splat) pair blended somewhere: remember it
-                if (lane == (int)(scount & 31u)) spend = (uint32_t)(pos - 1);
-                scount++;
-                if ((scount & 31u) == 0) qlist[scount - 32 + lane] = spend;
-            }
+            if (EMIT && (b0 || b1)) blended |= 1u << j;
+        }
+        if (EMIT) {     // one OR-reduction per round: the set lanes append their splat's list position, in order
+            const uint32_t any = __reduce_or_sync(0xffffffffu, blended);
+            if ((any >> lane) & 1u) qlist[scount + __popc(any & ((1u << lane) - 1u))] = (uint32_t)(base + lane);
+            scount += __popc(any);
         }
         // the slab written two rounds from now is this one: every lane must be done reading it
         __syncwarp();
     }
-    if (EMIT) {
-        if (lane < (int)(scount & 31u)) qlist[(scount & ~31u) + lane] = spend;
-        if (lane == 0) nsurv[4 * tile + warp] = scount;
-    }
+    if (EMIT && lane == 0) nsurv[4 * tile + warp] = scount;
     const size_t HW = (size_t)H * W;
     const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
     if (g.in0) {

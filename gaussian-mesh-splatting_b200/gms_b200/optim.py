@@ -18,7 +18,7 @@ REFERENCE_LRS = dict(vertices=0.0, alpha=0.001, f_dc=0.0025, f_rest=0.0025 / 20.
 
 
 class FlatAdam:
-    def __init__(self, groups: Sequence[dict], betas=(0.9, 0.999), eps: float = 1e-15, world: int = 1, rank: int = 0):
+    def __init__(self, groups: Sequence[dict], betas=(0.9, 0.999), eps: float = 1e-15, world: int = 1, rank: int = 0, kernel=None):
         """groups: dicts with `param` and either `lr`, or (`lr0`, `lr1`, `inner`, `period`) for the packed SH tensor.
         world > 1: SHARDED optimizer (ZeRO-1 style).  The gradient exchange is a reduce-scatter, every rank keeps Adam
         moments for and updates only its 1/world slice of the flat buffer, and an all-gather brings the updated
@@ -48,6 +48,7 @@ class FlatAdam:
             off += pad(k)
             self.ends.append(off)
         self.betas, self.eps, self.t = betas, eps, 0
+        self._kernel = kernel or self._cuda_kernel       # `kernel`: test hook (a callable taking the _adam_desc dict)
 
     @property
     def flat_grad(self) -> torch.Tensor:
@@ -56,41 +57,65 @@ class FlatAdam:
     def zero_grad(self):
         self.g.zero_()
 
+    # ---- the three stages of a step; `step()` strings them together (tests drive them under gloo with a stub kernel)
+    def _exchange_gradient(self):
+        """world > 1: average the flat gradient over the ranks and return (this rank's slice of it, parameter slice, flat
+        offset).  NCCL: one reduce-scatter that averages inside the collective (exact for power-of-two world sizes).
+        Backends without reduce-scatter / AVG (gloo: the CPU tests): all-reduce(SUM), scale, slice."""
+        import torch.distributed as dist
+        off = self.rank * self.shard
+        p_local = self.p[off:off + self.shard]
+        if self.world <= 1:
+            return self.g, self.p, 0
+        if dist.get_backend() == "nccl":
+            dist.reduce_scatter_tensor(self.g_shard, self.g, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(self.g, op=dist.ReduceOp.SUM)
+            self.g_shard.copy_(self.g[off:off + self.shard]).mul_(1.0 / self.world)
+        return self.g_shard, p_local, off
+
+    def _adam_desc(self, n, offset, p, g, zero_grad, zero_end):
+        """Everything gms_adam_step needs, as plain Python (the stub kernel of the CPU tests reads the same dict)."""
+        return dict(n=int(n), offset=int(offset), p=p, g=g, m=self.m, v=self.v, seg_end=list(self.ends),
+                    lr0=[float(g_.get("lr0", g_.get("lr", 0.0))) for g_ in self.groups],
+                    lr1=[float(g_.get("lr1", g_.get("lr", 0.0))) for g_ in self.groups],
+                    inner=[int(g_.get("inner", 1)) for g_ in self.groups], period=[int(g_.get("period", 0)) for g_ in self.groups],
+                    beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, step=self.t, zero_grad=int(zero_grad), zero_end=int(zero_end))
+
+    def _cuda_kernel(self, d):
+        a = _lib.AdamArgs()
+        a.n, a.offset = d["n"], d["offset"]
+        a.p, a.g, a.m, a.v = d["p"].data_ptr(), d["g"].data_ptr(), d["m"].data_ptr(), d["v"].data_ptr()
+        a.nseg = len(d["seg_end"])
+        for i in range(a.nseg):
+            a.seg_end[i], a.lr0[i], a.lr1[i], a.inner[i], a.period[i] = d["seg_end"][i], d["lr0"][i], d["lr1"][i], d["inner"][i], d["period"][i]
+        a.beta1, a.beta2, a.eps, a.step, a.zero_grad, a.zero_end = d["beta1"], d["beta2"], d["eps"], d["step"], d["zero_grad"], d["zero_end"]
+        dev = d["p"].device
+        if not d["p"].is_cuda:
+            raise RuntimeError("FlatAdam: CUDA tensors required (no CPU path in the product)")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gms_adam_step(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "gms_adam_step")
+
+    def _publish_parameters(self, p_local, zero_end):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.p, p_local)
+            (self.g if zero_end is None else self.g[:int(zero_end)]).zero_()
+
     def step(self, zero_end=None):
         """world == 1: one launch over the whole flat buffer (gradient zeroed in the same pass).
         world > 1: reduce-scatter(mean) -> Adam on the local slice -> all-gather of the parameters; the full gradient
         buffer is re-zeroed with one memset.
         zero_end: when the producer of the gradients OVERWRITES everything at flat indices >= zero_end each frame
         (gms_train_frame: all but the atomically accumulated vertex gradients), only [0, zero_end) is zeroed."""
-        import torch.distributed as dist
         self.t += 1
-        a = _lib.AdamArgs()
+        g, p_local, off = self._exchange_gradient()
         if self.world > 1:
-            # NCCL averages inside the collective (exact for power-of-two world sizes): no separate scaling pass
-            dist.reduce_scatter_tensor(self.g_shard, self.g, op=dist.ReduceOp.AVG)
-            off = self.rank * self.shard
-            p_local = self.p[off:off + self.shard]
-            a.n, a.offset = self.shard, off
-            a.p, a.g, a.m, a.v = p_local.data_ptr(), self.g_shard.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
-            a.zero_grad = 0            # g_shard is overwritten by the next reduce-scatter
+            d = self._adam_desc(self.shard, off, p_local, g, 0, 0)          # g_shard is overwritten by the next exchange
         else:
-            a.n, a.offset = self.n, 0
-            a.p, a.g, a.m, a.v = self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
-            a.zero_grad, a.zero_end = (1, 0) if zero_end is None else (2, int(zero_end))
-        a.nseg = len(self.groups)
-        for i, g in enumerate(self.groups):
-            a.seg_end[i] = self.ends[i]
-            a.lr0[i] = float(g.get("lr0", g.get("lr", 0.0)))
-            a.lr1[i] = float(g.get("lr1", g.get("lr", 0.0)))
-            a.inner[i] = int(g.get("inner", 1))
-            a.period[i] = int(g.get("period", 0))
-        a.beta1, a.beta2, a.eps, a.step = self.betas[0], self.betas[1], self.eps, self.t
-        dev = self.p.device
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().gms_adam_step(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "gms_adam_step")
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.p, p_local)
-            (self.g if zero_end is None else self.g[:int(zero_end)]).zero_()
+            d = self._adam_desc(self.n, 0, self.p, self.g, 1 if zero_end is None else 2, 0 if zero_end is None else zero_end)
+        self._kernel(d)
+        self._publish_parameters(p_local, zero_end)
 
     def zero_grad_partial(self, zero_end=None):
         (self.g if zero_end is None else self.g[:int(zero_end)]).zero_()

@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 import diff_gaussian_rasterization as dgr
 
-from .losses import training_loss, fused_training_loss
+from .losses import fused_training_loss
 from .model import MeshGaussianModel
 from .optim import FlatAdam, mesh_model_groups
 from .scenes import Camera
@@ -157,16 +157,18 @@ class MeshTrainer:
 
     fast=True  : fused expansion launch, packed SH features (zero-copy get_features), fused L1+SSIM loss kernels,
                  FlatAdam (one launch, zeroes the gradient) -- everything on the library's kernels except sigmoid.
-    fast=False : the reference's op sequence (two-step expansion + getters, ATen loss, torch.optim.Adam)."""
+    fast=False : the reference's op sequence (two-step expansion + getters, `loss_fn`, torch.optim.Adam) for A/B runs."""
 
     def __init__(self, model: MeshGaussianModel, bg: torch.Tensor, lambda_dssim: float = 0.2, world: int = 1,
-                 rank: int = 0, optimizer_step: bool = True, fast: bool = True, native: bool = False, sync_free: bool = True):
+                 rank: int = 0, optimizer_step: bool = True, fast: bool = True, native: bool = False, sync_free: bool = True,
+                 loss_fn=None):
         self.model, self.bg, self.lambda_dssim = model, bg, lambda_dssim
         self.world, self.rank = world, rank
         self.optimizer_step = optimizer_step
         self.fast = fast
         self.native = native and fast       # native: the whole frame is one C call (NativeFrame), no autograd
         self.sync_free = sync_free          # native frames after the first never synchronise with the host (NativeFrame)
+        self.loss_fn = loss_fn or fused_training_loss    # fast=False A/B arm: callers may pass an ATen loss (tests/aten_reference.py)
         self._frame = None
         if fast:
             self.opt = FlatAdam(mesh_model_groups(model), world=world, rank=rank)   # sharded over the ranks when world > 1
@@ -216,7 +218,7 @@ class MeshTrainer:
         _r.DIRECT_SH_GRAD = self.fast      # FlatAdam keeps .grad preallocated and zeroed: write dL/dshs in place
         try:
             image, radii, _ = render_frame(self.model, cam, self.bg, fused=self.fast)
-            loss = fused_training_loss(image, gt, self.lambda_dssim) if self.fast else training_loss(image, gt, self.lambda_dssim)
+            loss = fused_training_loss(image, gt, self.lambda_dssim) if self.fast else self.loss_fn(image, gt, self.lambda_dssim)
             loss.backward()
         finally:
             _r.DIRECT_SH_GRAD = prev       # never leak the in-place mode to other users of the rasterizer

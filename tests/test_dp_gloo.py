@@ -1,6 +1,7 @@
-"""CPU, world_size 2 over gloo: the host-side data-parallel logic (camera sharding, single flat-gradient all-reduce,
-replica consistency) with an oracle-backed stand-in for the per-rank frame gradient.  The CUDA kernels are not
-involved here (they are covered by -m gpu); what is tested is exactly the code path trainer.py runs around them."""
+"""CPU, world_size 2 over gloo: the host-side data-parallel logic -- camera sharding and the SHARDED FlatAdam
+(gms_b200/optim.py: gradient exchange -> Adam on this rank's slice -> all-gather of the parameters) -- driven through the
+product's own FlatAdam class with the CUDA kernel replaced by a float64 stub (`kernel=` hook) and a deterministic stand-in
+for the per-rank frame gradient.  The kernels themselves are covered by -m gpu (tests/test_gpu_step.py, tests/test_gpu_dist.py)."""
 import os
 import socket
 
@@ -54,3 +55,77 @@ def test_flat_gradient_all_reduce_world2():
     expect = sum(torch.randn(out[0][1].numel(), generator=torch.Generator().manual_seed(100 + c)) for c in cams) / world
     for r in range(world):
         torch.testing.assert_close(out[r][1], expect)      # every replica ends with the same averaged gradient
+
+
+def _adam_stub(d):
+    """Float64 restatement of gms_adam_step on the descriptor FlatAdam hands to its kernel (per-segment learning rates,
+    DC/rest phase of the packed SH segment, shard offset)."""
+    n, off = d["n"], d["offset"]
+    idx = torch.arange(off, off + n)
+    lr = torch.zeros(n, dtype=torch.float64)
+    start = 0
+    for end, lr0, lr1, inner, period in zip(d["seg_end"], d["lr0"], d["lr1"], d["inner"], d["period"]):
+        sel = (idx >= start) & (idx < end)
+        if period > 0:
+            phase = ((idx - start) // inner) % period
+            lr[sel] = torch.where(phase[sel] == 0, lr0, lr1).double() if sel.any() else lr[sel]
+        else:
+            lr[sel] = lr0
+        start = end
+    g = d["g"][:n].double()
+    m = d["beta1"] * d["m"][:n].double() + (1 - d["beta1"]) * g
+    v = d["beta2"] * d["v"][:n].double() + (1 - d["beta2"]) * g * g
+    step = lr / (1 - d["beta1"] ** d["step"])
+    p = d["p"][:n].double() - step * m / (v.sqrt() / (1 - d["beta2"] ** d["step"]) ** 0.5 + d["eps"])
+    d["p"][:n].copy_(p.float()); d["m"][:n].copy_(m.float()); d["v"][:n].copy_(v.float())
+    if d["zero_grad"] == 1:
+        d["g"][:n].zero_()
+    elif d["zero_grad"] == 2:
+        k = max(0, min(n, d["zero_end"] - off))
+        d["g"][:k].zero_()
+
+
+def _make_groups(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda *s: torch.nn.Parameter(torch.randn(*s, generator=g))
+    return [dict(param=mk(30, 3), lr=1e-4, name="vertices"), dict(param=mk(20, 2, 3), lr=1e-3, name="alpha"),
+            dict(param=mk(40, 16, 3), lr0=2.5e-3, lr1=1.25e-4, inner=3, period=16, name="features"),
+            dict(param=mk(40, 1), lr=5e-2, name="opacity"), dict(param=mk(40, 1), lr=5e-3, name="scaling")]
+
+
+def _frame_gradient(n, cam, step):
+    return torch.randn(n, generator=torch.Generator().manual_seed(1000 * step + cam))
+
+
+def _flat_adam_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gms_b200.optim import FlatAdam
+    opt = FlatAdam(_make_groups(), world=world, rank=rank, kernel=_adam_stub)
+    for step in range(3):
+        cam = shard_cameras(8, step, rank, world)
+        opt.g.copy_(_frame_gradient(opt.n, cam, step))
+        opt.step(zero_end=opt.ends[0])
+    out[rank] = (opt.p.clone(), opt.g.clone(), opt.shard, opt.n)
+    dist.destroy_process_group()
+
+
+def test_sharded_flat_adam_world2_equals_single_process():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_flat_adam_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    from gms_b200.optim import FlatAdam
+    ref = FlatAdam(_make_groups(), world=1, rank=0, kernel=_adam_stub)
+    n = out[0][3]
+    assert out[0][2] * world == n and out[0][2] % 64 == 0            # equal, 256-byte aligned shards
+    pad = n - ref.n
+    for step in range(3):
+        cams = [shard_cameras(8, step, r, world) for r in range(world)]
+        gavg = sum(_frame_gradient(n, c, step) for c in cams) / world
+        ref.g.copy_(gavg[:ref.n] if pad else gavg)
+        ref.step(zero_end=ref.ends[0])
+    for r in range(world):
+        torch.testing.assert_close(out[r][0][:ref.n], ref.p, rtol=1e-6, atol=1e-7)     # every replica == the single-process optimiser
+        assert torch.equal(out[r][0], out[0][0])                                         # replicas identical bit for bit
+        assert float(out[r][1][:ref.ends[0]].abs().max()) == 0.0                         # the vertex-gradient segment was re-zeroed

@@ -123,8 +123,8 @@ def test_projection_matches_reference_geom_transform(golden_dir):
 
 
 def test_loss_restatement_matches_reference_loss_utils(golden_dir):
-    """gms_b200.losses.training_loss (the fp32 reference of the fused loss kernel) == utils/loss_utils.py."""
-    from gms_b200 import losses
+    """tests/aten_reference.training_loss (the fp32 reference of the fused loss kernel) == utils/loss_utils.py."""
+    import aten_reference as losses
     g = _load(golden_dir, "loss.npz")
     a = torch.tensor(g["img"], requires_grad=True); b = torch.tensor(g["gt"])
     assert abs(losses.l1_loss(a, b).item() - float(g["l1"])) < 1e-7
