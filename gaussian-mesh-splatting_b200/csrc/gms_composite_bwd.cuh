@@ -71,6 +71,9 @@ k_composite_bwd5(const int2* __restrict__ ranges, const int* __restrict__ tile_o
     int rk8 = 8 * (lane / NV), ri = lane % NV;            // lane r sums panel row r = (pending splat r / NV, value r % NV)
     asm volatile("" : "+r"(rk8), "+r"(ri));
     int pend = 0, pj = 0;                                 // pending splats in the panel, their slab indices (8 bits each)
+    (void)pend; (void)pj; (void)rk8;
+    int rdiv = lane / NV;                                  // panel row `lane` belongs to splat j0 - rdiv of the current group
+    asm volatile("" : "+r"(rdiv));
     const int cnt = (int)nsurv[4 * tile + warp];          // (quad, splat) pairs that blended in the forward pass
     if (cnt <= 0) return;
     const uint32_t* __restrict__ ql = surv + 4 * (size_t)rng.x + (size_t)warp * (rng.y - rng.x);
@@ -111,65 +114,82 @@ k_composite_bwd5(const int2* __restrict__ ranges, const int* __restrict__ tile_o
     for (int b = nb - 1; b >= 0; b--) {
         S.id[lane] = id_cur; S.pos[lane] = pos_cur;
         if (id_cur >= 0) gms_slab3_store(reinterpret_cast<GmsSlab3&>(S), lane, ra, rb, rc);
-        uint32_t m = __ballot_sync(0xffffffffu, id_cur >= 0);
+        const int nin = min(GMS_WB, cnt - b * GMS_WB);          // staged survivors this round (only the first round is partial)
         id_cur = id_nx; pos_cur = pos_nx;
         if (id_cur >= 0) { ra = recs[3 * id_cur]; rb = recs[3 * id_cur + 1]; rc = recs[3 * id_cur + 2]; }
         if (b >= 2) { pos_nx = (int)ql[(b - 2) * GMS_WB + lane]; id_nx = (int)plist[pos_nx]; } else { pos_nx = -1; id_nx = -1; }
         __syncwarp();
-        const uint32_t touched_all = m;
-        uint32_t touched = 0;
-        while (m) {
-            const int j = 31 - __clz(m);
-            m &= ~(1u << j);
-            const int pos = S.pos[j];
-            const float4 Q0 = S.q0[j], Q1 = S.q1[j], Q2 = S.q2[j];
-            f2 dx, dy;
-            const f2 power = gms_power2(Q0, Q1, Q2, npx, npy, dx, dy);
-            const f2 sc = f2mul(power, make_float2(GMS_LOG2E, GMS_LOG2E));
-            const f2 G = make_float2(gms_ex2(sc.x), gms_ex2(sc.y));
-            const f2 araw = f2mul(make_float2(Q2.z, Q2.w), G);
-            const float a0 = fminf(GMS_ALPHA_MAX, araw.x), a1 = fminf(GMS_ALPHA_MAX, araw.y);
-            const bool v0 = pos < lastA && power.x <= 0.0f && a0 >= GMS_ALPHA_MIN;
-            const bool v1 = pos < lastB && power.y <= 0.0f && a1 >= GMS_ALPHA_MIN;
-            const float4 Q3 = S.q3[j], Q4 = S.q4[j];
-            const f2 alpha = make_float2(v0 ? a0 : 0.f, v1 ? a1 : 0.f);
-            const f2 oma = f2fma(alpha, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
-            const f2 inv = make_float2(gms_rcp(oma.x), gms_rcp(oma.y));
-            T = f2mul(T, inv);
-            const f2 w = f2mul(alpha, T);
-            const f2 cr = make_float2(Q3.x, Q3.y), cg = make_float2(Q3.z, Q3.w), cb = make_float2(Q4.x, Q4.y), cd = make_float2(Q4.z, Q4.w);
-            const f2 neg1 = make_float2(-1.f, -1.f);
-            // dL/dalpha = sum_c (c - B_c) * dL/dC_c   (then * T, + background term)
-            f2 dLa = f2mul(f2fma(Br, neg1, cr), dpr);
-            dLa = f2fma(f2fma(Bg, neg1, cg), dpg, dLa);
-            dLa = f2fma(f2fma(Bb, neg1, cb), dpb, dLa);
-            if (DEPTH) dLa = f2fma(f2fma(Bd, neg1, cd), dpd, dLa);
-            // advance "behind": B <- alpha*c + (1-alpha)*B
-            Br = f2fma(alpha, cr, f2mul(oma, Br)); Bg = f2fma(alpha, cg, f2mul(oma, Bg));
-            Bb = f2fma(alpha, cb, f2mul(oma, Bb));
-            if (DEPTH) Bd = f2fma(alpha, cd, f2mul(oma, Bd));
-            dLa = f2mul(dLa, T);
-            dLa = f2fma(f2mul(nTfin, inv), bgdot, dLa);
-            f2 q = f2mul(dLa, G);
-            q.x = v0 ? q.x : 0.f; q.y = v1 ? q.y : 0.f;
-            const f2 qx = f2mul(q, dx), qy = f2mul(q, dy);
-            const f2 pxx = f2mul(qx, dx), pxy = f2mul(qx, dy), pyy = f2mul(qy, dy);
-            const f2 wr = f2mul(w, dpr), wg = f2mul(w, dpg), wb = f2mul(w, dpb);
-            const f2 wd = DEPTH ? f2mul(w, dpd) : make_float2(0.f, 0.f);
-            float v[10];
-            v[0] = qx.x + qx.y; v[1] = qy.x + qy.y; v[2] = pxx.x + pxx.y; v[3] = pxy.x + pxy.y; v[4] = pyy.x + pyy.y;
-            v[5] = q.x + q.y; v[6] = wr.x + wr.y; v[7] = wg.x + wg.y; v[8] = wb.x + wb.y; v[9] = wd.x + wd.y;
-            {
-                float* col = red + (pend * NV) * GMS_RED_STRIDE + lane;
+        // Groups of up to three splats = one panel.  The alpha evaluation of a group's splats does not depend on the
+        // transmittance / colour-behind recurrence, so the three evaluations are issued together (independent chains of
+        // LDS -> FMUL2/FFMA2 -> EX2 -> RCP) ahead of the serial recurrence: more instruction-level parallelism per warp.
+        for (int j0 = nin - 1; j0 >= 0; j0 -= 3) {
+            f2 e_dx[3], e_dy[3], e_G[3], e_al[3], e_inv[3], e_oma[3];
+            bool e_v0[3], e_v1[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int jj = max(j0 - u, 0);                  // (tail group: re-evaluates splat 0, results unused)
+                const int pos = S.pos[jj];
+                const float4 Q0 = S.q0[jj], Q1 = S.q1[jj], Q2 = S.q2[jj];
+                const f2 power = gms_power2(Q0, Q1, Q2, npx, npy, e_dx[u], e_dy[u]);
+                const f2 sc = f2mul(power, make_float2(GMS_LOG2E, GMS_LOG2E));
+                e_G[u] = make_float2(gms_ex2(sc.x), gms_ex2(sc.y));
+                const f2 araw = f2mul(make_float2(Q2.z, Q2.w), e_G[u]);
+                const float a0 = fminf(GMS_ALPHA_MAX, araw.x), a1 = fminf(GMS_ALPHA_MAX, araw.y);
+                e_v0[u] = pos < lastA && power.x <= 0.0f && a0 >= GMS_ALPHA_MIN;
+                e_v1[u] = pos < lastB && power.y <= 0.0f && a1 >= GMS_ALPHA_MIN;
+                e_al[u] = make_float2(e_v0[u] ? a0 : 0.f, e_v1[u] ? a1 : 0.f);
+                e_oma[u] = f2fma(e_al[u], make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+                e_inv[u] = make_float2(gms_rcp(e_oma[u].x), gms_rcp(e_oma[u].y));
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                if (j0 - u < 0) break;                          // uniform
+                const int jj = j0 - u;
+                const float4 Q3 = S.q3[jj], Q4 = S.q4[jj];
+                const f2 alpha = e_al[u], oma = e_oma[u], inv = e_inv[u], dx = e_dx[u], dy = e_dy[u];
+                T = f2mul(T, inv);
+                const f2 w = f2mul(alpha, T);
+                const f2 cr = make_float2(Q3.x, Q3.y), cg = make_float2(Q3.z, Q3.w), cb = make_float2(Q4.x, Q4.y), cd = make_float2(Q4.z, Q4.w);
+                const f2 neg1 = make_float2(-1.f, -1.f);
+                // dL/dalpha = sum_c (c - B_c) * dL/dC_c   (then * T, + background term)
+                f2 dLa = f2mul(f2fma(Br, neg1, cr), dpr);
+                dLa = f2fma(f2fma(Bg, neg1, cg), dpg, dLa);
+                dLa = f2fma(f2fma(Bb, neg1, cb), dpb, dLa);
+                if (DEPTH) dLa = f2fma(f2fma(Bd, neg1, cd), dpd, dLa);
+                // advance "behind": B <- alpha*c + (1-alpha)*B
+                Br = f2fma(alpha, cr, f2mul(oma, Br)); Bg = f2fma(alpha, cg, f2mul(oma, Bg));
+                Bb = f2fma(alpha, cb, f2mul(oma, Bb));
+                if (DEPTH) Bd = f2fma(alpha, cd, f2mul(oma, Bd));
+                dLa = f2mul(dLa, T);
+                dLa = f2fma(f2mul(nTfin, inv), bgdot, dLa);
+                f2 q = f2mul(dLa, e_G[u]);
+                q.x = e_v0[u] ? q.x : 0.f; q.y = e_v1[u] ? q.y : 0.f;
+                const f2 qx = f2mul(q, dx), qy = f2mul(q, dy);
+                const f2 pxx = f2mul(qx, dx), pxy = f2mul(qx, dy), pyy = f2mul(qy, dy);
+                const f2 wr = f2mul(w, dpr), wg = f2mul(w, dpg), wb = f2mul(w, dpb);
+                const f2 wd = DEPTH ? f2mul(w, dpd) : make_float2(0.f, 0.f);
+                float v[10];
+                v[0] = qx.x + qx.y; v[1] = qy.x + qy.y; v[2] = pxx.x + pxx.y; v[3] = pxy.x + pxy.y; v[4] = pyy.x + pyy.y;
+                v[5] = q.x + q.y; v[6] = wr.x + wr.y; v[7] = wg.x + wg.y; v[8] = wb.x + wb.y; v[9] = wd.x + wd.y;
+                float* col = red + (u * NV) * GMS_RED_STRIDE + lane;
 #pragma unroll
                 for (int i = 0; i < NV; i++) col[i * GMS_RED_STRIDE] = v[i];
-                pj |= j << (8 * pend);
-                if (++pend == 3) { gms_red_flush<NV>(red, S.part, pj, 3 * NV, lane, rk8, ri); pend = 0; pj = 0; }
             }
-            touched |= 1u << j;
+            {   // row sums of the panel: lane r < np * NV adds up value (r % NV) of splat j0 - r / NV
+                const int np = min(3, j0 + 1);
+                __syncwarp();
+                if (lane < np * NV) {
+                    const float4* rowp = reinterpret_cast<const float4*>(red + lane * GMS_RED_STRIDE);
+                    const float4 a4 = rowp[0];
+                    float s0 = a4.x + a4.y, s1 = a4.z + a4.w;
+#pragma unroll
+                    for (int c = 1; c < 8; c++) { const float4 t4 = rowp[c]; s0 += t4.x; s1 += t4.z; s0 += t4.y; s1 += t4.w; }
+                    S.part[j0 - rdiv][ri] = s0 + s1;
+                }
+                __syncwarp();
+            }
         }
-        touched = touched_all;
-        if (pend) { gms_red_flush<NV>(red, S.part, pj, pend * NV, lane, rk8, ri); pend = 0; pj = 0; }
+        const uint32_t touched = nin >= 32 ? 0xffffffffu : ((1u << nin) - 1u);
         __syncwarp();
         if ((touched >> lane) & 1u) {
             const int id = S.id[lane];
