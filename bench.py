@@ -83,11 +83,12 @@ METRIC = {
 CPU_TILE_STRIDE = {"gs_mesh_1M_1080p": 8, "gs_multi_mesh_2M_1080p": 16, "gs_mesh_500k_1080p": 8, "gs_mesh_100k_800": 2}
 ALGO_BYTES = {  # algorithmic bytes per unit, SURVEY.md section 8(d) / DESIGN.md "Roofline accounting"
     "composite_bwd": dict(N=84, px=24), "composite_fwd": dict(N=44, px=24),
-    "preprocess_fwd": dict(P=311 + 8), "preprocess_bwd": dict(P=563),
+    "preprocess_fwd": dict(P=311 + 8), "preprocess_bwd": dict(P=563 - 192 + 12),     # factored SH gradient: 12 B colour gradient instead of 192 B of rows
     "expand_fwd": dict(P=56, F=60), "expand_bwd": dict(P=56, F=36),
     "emit_dups": dict(P=28, N=8), "cub_sort_tiles": dict(P=2 * 12, N=4), "cub_sort_depth": dict(P=16), "tile_ranges": dict(N=4),
     "cub_scan_tiles": dict(P=12), "ssim_stats": dict(px=3 * (8 + 12)), "ssim_grad": dict(px=3 * (12 + 8 + 4)),
-    "adam": dict(P=53 * 28),      # p, g, m, v read + p, m, v written = 28 B/parameter (only the vertex gradients are re-zeroed)
+    "adam": dict(P=5 * 28 + 48 * 24 + 12 + 12),   # 5 non-SH parameters/Gaussian at 28 B (p, g, m, v read; p, m, v written) + 48 SH parameters at
+                                                  # 24 B (no gradient read: rebuilt from 12 B of colour gradient per rank and the 12 B centre)
 }
 
 
@@ -745,7 +746,7 @@ def main():
         if cnt:
             ab = sum(ALGO_BYTES.get(name, {}).get(u, 0) * units[u] for u in units)
             if name == "adam":
-                ab /= world             # sharded optimizer: every rank updates 1/world of the flat buffer
+                ab += 12 * (world - 1) * P          # replicated factored optimizer: one more 12 B colour gradient per extra rank
             per_kernel[name] = {"ms": ms / cnt, "launches_per_step": cnt / min(K_, 10), "algo_bytes": ab,
                                 "gbs": (ab / (ms / cnt * 1e-3) / 1e9) if ms > 0 else None}
     if "cub_sort_tiles" in per_kernel and not any(o.startswith("bin_impl=0") for o in args.opt):

@@ -340,7 +340,7 @@ GMS_HD void gms_sh_backward(int deg, int M, const float* mean, const float* camp
     for (int k = 0; k < 16; k++) t[k] = (k < nc) ? (sh[3 * k] * g[0] + sh[3 * k + 1] * g[1] + sh[3 * k + 2] * g[2]) : 0.f;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        if (k < M) {
+        if (dsh && k < M) {     // dsh == NULL: the caller exchanges the masked colour gradient instead (factored SH gradient)
             const float bk = k < nc ? B[k] : 0.f;
             dsh[3 * k + 0] = bk * g[0]; dsh[3 * k + 1] = bk * g[1]; dsh[3 * k + 2] = bk * g[2];
         }

@@ -50,7 +50,7 @@ class RasterSaved(C.Structure):
 class RasterGrads(C.Structure):
     _fields_ = [("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dopacities", C.c_void_p),
                 ("dL_dshs", C.c_void_p), ("dL_dcolors_precomp", C.c_void_p), ("dL_dscales", C.c_void_p),
-                ("dL_drotations", C.c_void_p), ("dL_dcov3D_precomp", C.c_void_p)]
+                ("dL_drotations", C.c_void_p), ("dL_dcov3D_precomp", C.c_void_p), ("dL_dcolors_sh", C.c_void_p)]
 
 
 class DebugViews(C.Structure):
@@ -108,7 +108,19 @@ class FrameArgs(C.Structure):
                 ("d_features", C.c_void_p), ("d_opacity_raw", C.c_void_p),
                 ("settings", RasterSettings), ("gt", C.c_void_p), ("lambda_dssim", C.c_float), ("loss", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("num_rendered", C.POINTER(C.c_int64)),
-                ("binning_capacity", C.c_int64), ("n_host_mapped", C.c_void_p)]
+                ("binning_capacity", C.c_int64), ("n_host_mapped", C.c_void_p), ("d_color_sh", C.c_void_p)]
+
+
+class FrameView(C.Structure):
+    _fields_ = [("xyz", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p), ("opacities", C.c_void_p),
+                ("radii", C.c_void_p), ("image", C.c_void_p), ("invdepth", C.c_void_p)]
+
+
+class AdamShArgs(C.Structure):
+    _fields_ = [("P", C.c_int32), ("M", C.c_int32), ("sh_degree", C.c_int32), ("R", C.c_int32), ("xyz", C.c_void_p),
+                ("exchange", C.c_void_p), ("slot_floats", C.c_int64), ("grad_scale", C.c_float), ("p", C.c_void_p),
+                ("m", C.c_void_p), ("v", C.c_void_p), ("lr_dc", C.c_double), ("lr_rest", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("step", C.c_int32)]
 
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
@@ -119,7 +131,7 @@ ABI_SYMBOLS = ["gms_scratch_bytes", "gms_binning_bytes", "gms_rasterize_forward"
                "gms_expand_backward", "gms_last_error", "gms_version", "gms_launch_count", "gms_set_option",
                "gms_kernel_times", "gms_loss_scratch_bytes", "gms_l1_ssim_loss", "gms_adam_step",
                "gms_frame_workspace_bytes", "gms_train_frame", "gms_points_expand_forward",
-               "gms_points_prepare_vertices", "gms_image_quantize", "gms_image_dequantize"]
+               "gms_points_prepare_vertices", "gms_image_quantize", "gms_image_dequantize", "gms_adam_sh_factored", "gms_frame_views"]
 
 _lib = None
 
@@ -165,6 +177,8 @@ def lib():
     L.gms_points_prepare_vertices.argtypes = [C.POINTER(PointsVerticesArgs), C.c_void_p]
     L.gms_image_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.gms_image_dequantize.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.gms_adam_sh_factored.argtypes = [C.POINTER(AdamShArgs), C.c_void_p]
+    L.gms_frame_views.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(FrameView)]
     L.gms_frame_workspace_bytes.restype = C.c_size_t
     L.gms_frame_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.gms_train_frame.argtypes = [C.POINTER(FrameArgs), ALLOC_FN, C.c_void_p, C.c_void_p]

@@ -18,13 +18,21 @@ REFERENCE_LRS = dict(vertices=0.0, alpha=0.001, f_dc=0.0025, f_rest=0.0025 / 20.
 
 
 class FlatAdam:
-    def __init__(self, groups: Sequence[dict], betas=(0.9, 0.999), eps: float = 1e-15, world: int = 1, rank: int = 0, kernel=None):
+    def __init__(self, groups: Sequence[dict], betas=(0.9, 0.999), eps: float = 1e-15, world: int = 1, rank: int = 0, kernel=None,
+                 sh_factored: bool = False):
         """groups: dicts with `param` and either `lr`, or (`lr0`, `lr1`, `inner`, `period`) for the packed SH tensor.
         world > 1: SHARDED optimizer (ZeRO-1 style).  The gradient exchange is a reduce-scatter, every rank keeps Adam
         moments for and updates only its 1/world slice of the flat buffer, and an all-gather brings the updated
         parameters back -- the same bytes on NVLink as an all-reduce, but the 28 B/parameter Adam pass shrinks by `world`."""
         self.groups = list(groups)
         self.world, self.rank = int(world), int(rank)
+        # sh_factored: the LAST group is the packed SH tensor [P,16,3] and its gradient arrives as factors (step(sh=...)):
+        # the optimizer is then REPLICATED (full moments on every rank), the exchange is an all-reduce of the other groups'
+        # gradients (32 B/Gaussian) plus an all-gather of the colour gradients (12 B/Gaussian/rank), and no parameter
+        # all-gather follows.  Dense mode (default): sharded optimizer, reduce-scatter + all-gather of everything.
+        self.sh_factored = bool(sh_factored)
+        if self.sh_factored and not ("period" in self.groups[-1] and self.groups[-1]["param"].dim() == 3):
+            raise ValueError("sh_factored needs the packed SH tensor as the last group (mesh_model_groups(features_last=True))")
         assert 1 <= len(self.groups) <= 8
         params = [g["param"] for g in self.groups]
         dev = params[0].device
@@ -35,8 +43,9 @@ class FlatAdam:
         self.shard = n // self.world
         self.p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.g = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.m = torch.zeros(self.shard, dtype=torch.float32, device=dev)      # moments: this rank's slice only
-        self.v = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        nm = n if self.sh_factored else self.shard
+        self.m = torch.zeros(nm, dtype=torch.float32, device=dev)      # moments: this rank's slice only (dense mode)
+        self.v = torch.zeros(nm, dtype=torch.float32, device=dev)
         self.g_shard = torch.zeros(self.shard, dtype=torch.float32, device=dev) if self.world > 1 else None
         off = 0
         self.ends = []
@@ -102,13 +111,47 @@ class FlatAdam:
             dist.all_gather_into_tensor(self.p, p_local)
             (self.g if zero_end is None else self.g[:int(zero_end)]).zero_()
 
-    def step(self, zero_end=None):
-        """world == 1: one launch over the whole flat buffer (gradient zeroed in the same pass).
+    def _step_factored(self, zero_end, sh):
+        """sh = dict(xyz=<device pointer>, exchange=<[R, slot] float tensor: slot r = colour gradients + camera centre of rank r's frame>,
+        degree=<active SH degree>)."""
+        import torch.distributed as dist
+        prefix = self.ends[-2]                       # everything but the SH group
+        ex = sh["exchange"]
+        if self.world > 1:
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(self.g[:prefix], op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(self.g[:prefix], op=dist.ReduceOp.SUM); self.g[:prefix].mul_(1.0 / self.world)
+            dist.all_gather_into_tensor(ex.view(-1), ex[self.rank])
+        d = self._adam_desc(prefix, 0, self.p, self.g, 1 if zero_end is None else 2, 0 if zero_end is None else zero_end)
+        for k in ("seg_end", "lr0", "lr1", "inner", "period"):
+            d[k] = d[k][:-1]
+        self._kernel(d)
+        gsh = self.groups[-1]
+        f = gsh["param"]
+        off = self.ends[-2]
+        a = _lib.AdamShArgs()
+        a.P, a.M, a.sh_degree, a.R = f.shape[0], f.shape[1], int(sh["degree"]), ex.shape[0]
+        a.xyz, a.exchange, a.slot_floats, a.grad_scale = int(sh["xyz"]), ex.data_ptr(), ex.shape[1], 1.0 / ex.shape[0]
+        a.p, a.m, a.v = f.data_ptr(), self.m[off:].data_ptr(), self.v[off:].data_ptr()
+        a.lr_dc, a.lr_rest = float(gsh["lr0"]), float(gsh["lr1"])
+        a.beta1, a.beta2, a.eps, a.step = self.betas[0], self.betas[1], self.eps, self.t
+        dev = f.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gms_adam_sh_factored(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "gms_adam_sh_factored")
+
+    def step(self, zero_end=None, sh=None):
+        """sh given (sh_factored optimizers): see _step_factored.  Otherwise:
+        world == 1: one launch over the whole flat buffer (gradient zeroed in the same pass).
         world > 1: reduce-scatter(mean) -> Adam on the local slice -> all-gather of the parameters; the full gradient
         buffer is re-zeroed with one memset.
         zero_end: when the producer of the gradients OVERWRITES everything at flat indices >= zero_end each frame
         (gms_train_frame: all but the atomically accumulated vertex gradients), only [0, zero_end) is zeroed."""
         self.t += 1
+        if self.sh_factored:
+            if sh is None:
+                raise ValueError("this FlatAdam was built with sh_factored=True: step() needs the SH gradient factors (sh=...)")
+            return self._step_factored(zero_end, sh)
         g, p_local, off = self._exchange_gradient()
         if self.world > 1:
             d = self._adam_desc(self.shard, off, p_local, g, 0, 0)          # g_shard is overwritten by the next exchange
@@ -121,13 +164,16 @@ class FlatAdam:
         (self.g if zero_end is None else self.g[:int(zero_end)]).zero_()
 
 
-def mesh_model_groups(model, lrs=REFERENCE_LRS) -> List[dict]:
-    """Parameter groups of a MeshGaussianModel in the reference's order and learning rates."""
+def mesh_model_groups(model, lrs=REFERENCE_LRS, features_last: bool = False) -> List[dict]:
+    """Parameter groups of a MeshGaussianModel with the reference's learning rates; the reference's order (vertices, alpha,
+    f_dc, f_rest, opacity, scaling -- gaussian_mesh_model.py:174-181), or with the packed SH tensor moved to the end
+    (features_last: what FlatAdam(sh_factored=True) needs; the order of Adam groups has no numerical meaning)."""
     g = [dict(param=model.vertices, lr=lrs["vertices"], name="vertices"), dict(param=model._alpha, lr=lrs["alpha"], name="alpha")]
+    feats = []
     if model._features is not None:
         M = model._features.shape[1]
-        g.append(dict(param=model._features, lr0=lrs["f_dc"], lr1=lrs["f_rest"], inner=3, period=M, name="features"))
+        feats.append(dict(param=model._features, lr0=lrs["f_dc"], lr1=lrs["f_rest"], inner=3, period=M, name="features"))
     else:
-        g += [dict(param=model._features_dc, lr=lrs["f_dc"], name="f_dc"), dict(param=model._features_rest, lr=lrs["f_rest"], name="f_rest")]
-    g += [dict(param=model._opacity, lr=lrs["opacity"], name="opacity"), dict(param=model._scale, lr=lrs["scaling"], name="scaling")]
-    return g
+        feats += [dict(param=model._features_dc, lr=lrs["f_dc"], name="f_dc"), dict(param=model._features_rest, lr=lrs["f_rest"], name="f_rest")]
+    rest = [dict(param=model._opacity, lr=lrs["opacity"], name="opacity"), dict(param=model._scale, lr=lrs["scaling"], name="scaling")]
+    return g + (rest + feats if features_last else feats + rest)

@@ -58,7 +58,8 @@ class NativeFrame:
     A frame whose N exceeds the capacity renders the background with zero gradients and raises the flag; the next run()
     grows the region, counts the event in `overflows` and carries on."""
 
-    def __init__(self, model: MeshGaussianModel, width: int, height: int, lambda_dssim: float = 0.2, sync_free: bool = True):
+    def __init__(self, model: MeshGaussianModel, width: int, height: int, lambda_dssim: float = 0.2, sync_free: bool = True,
+                 world: int = 1, rank: int = 0):
         import ctypes as C
         from . import _lib
         assert model._features is not None, "NativeFrame needs packed SH features"
@@ -73,6 +74,11 @@ class NativeFrame:
         self.capacity = 0                       # duplicates the binning region is sized for (0: not known yet)
         self.n_host = torch.zeros(2, dtype=torch.int32).pin_memory()     # written by k_bin_tiles: N, overflow flag
         self.overflows = 0
+        # factored SH gradient (run(..., factored=True)): slot r of `exchange` = [3P colour gradients | camera centre | pad] of
+        # rank r's frame; this rank's frame writes slot `rank`, FlatAdam(sh_factored=True) all-gathers and consumes the rest
+        self.world, self.rank = int(world), int(rank)
+        self.slot = (3 * P + 3 + 63) // 64 * 64
+        self.exchange = None
         self._check_model()
         scratch = {}
         self._scratch = scratch
@@ -109,7 +115,15 @@ class NativeFrame:
         """N of the most recent frame whose binning kernel has run (no synchronisation: may lag by a frame)."""
         return int(self.n_host[0]) if (self.sync_free and self.capacity > 0) else int(self.n_rendered.value)
 
-    def run(self, cam: Camera, gt: torch.Tensor, bg: torch.Tensor) -> torch.Tensor:
+    def sh_factors(self) -> dict:
+        """What FlatAdam.step(sh=...) needs after a factored frame."""
+        import ctypes as C
+        from . import _lib
+        v = _lib.FrameView()
+        _lib.check(_lib.lib().gms_frame_views(self.ws.data_ptr(), self.model._scale.shape[0], self.W, self.H, C.byref(v)), "gms_frame_views")
+        return dict(xyz=v.xyz, exchange=self.exchange, degree=self.model.active_sh_degree)
+
+    def run(self, cam: Camera, gt: torch.Tensor, bg: torch.Tensor, factored: bool = False) -> torch.Tensor:
         import ctypes as C
         from . import _lib
         for t, what in ((gt, "gt"), (bg, "bg"), (cam.world_view_transform, "camera matrices"), (cam.full_proj_transform, "camera matrices"),
@@ -127,6 +141,10 @@ class NativeFrame:
         a.features, a.opacity_raw, a.eps = m._features.data_ptr(), m._opacity.data_ptr(), m.eps_s0
         a.d_vertices, a.d_alpha_raw, a.d_scale_raw = m.vertices.grad.data_ptr(), m._alpha.grad.data_ptr(), m._scale.grad.data_ptr()
         a.d_features, a.d_opacity_raw = m._features.grad.data_ptr(), m._opacity.grad.data_ptr()
+        if factored:        # no SH gradient rows: the colour gradient + camera centre go to this rank's exchange slot
+            if self.exchange is None:
+                self.exchange = torch.zeros(self.world, self.slot, dtype=torch.float32, device=self.dev)
+            a.d_features, a.d_color_sh = None, self.exchange[self.rank].data_ptr()
         s = a.settings
         s.image_height, s.image_width, s.tanfovx, s.tanfovy = self.H, self.W, cam.tanfovx, cam.tanfovy
         s.bg, s.scale_modifier = bg.data_ptr(), 1.0
@@ -161,7 +179,7 @@ class MeshTrainer:
 
     def __init__(self, model: MeshGaussianModel, bg: torch.Tensor, lambda_dssim: float = 0.2, world: int = 1,
                  rank: int = 0, optimizer_step: bool = True, fast: bool = True, native: bool = False, sync_free: bool = True,
-                 loss_fn=None):
+                 loss_fn=None, sh_factored: bool = True):
         self.model, self.bg, self.lambda_dssim = model, bg, lambda_dssim
         self.world, self.rank = world, rank
         self.optimizer_step = optimizer_step
@@ -170,8 +188,12 @@ class MeshTrainer:
         self.sync_free = sync_free          # native frames after the first never synchronise with the host (NativeFrame)
         self.loss_fn = loss_fn or fused_training_loss    # fast=False A/B arm: callers may pass an ATen loss (tests/aten_reference.py)
         self._frame = None
+        self.sh_factored = False
         if fast:
-            self.opt = FlatAdam(mesh_model_groups(model), world=world, rank=rank)   # sharded over the ranks when world > 1
+            # native frames hand the SH gradient over as factors (12 B instead of 192 B per Gaussian; replicated optimizer);
+            # the autograd-driven path materialises it (dense mode: sharded optimizer when world > 1)
+            self.sh_factored = bool(sh_factored) and self.native and model._features is not None and model._features.shape[1] == 16
+            self.opt = FlatAdam(mesh_model_groups(model, features_last=self.sh_factored), world=world, rank=rank, sh_factored=self.sh_factored)
             self.flat_grad = self.opt.flat_grad
         else:
             self.opt = model.training_setup()
@@ -198,8 +220,10 @@ class MeshTrainer:
         the loss every step waits only for the frame, and its next step's launch overhead overlaps the Adam pass."""
         if self.native:
             if self._frame is None:
-                self._frame = NativeFrame(self.model, cam.image_width, cam.image_height, self.lambda_dssim, sync_free=self.sync_free)
-            loss = self._frame.run(cam, gt, self.bg)
+                self._frame = NativeFrame(self.model, cam.image_width, cam.image_height, self.lambda_dssim, sync_free=self.sync_free,
+                                          world=self.world, rank=self.rank)
+            factored = self.sh_factored and self.optimizer_step      # without an optimizer step the full gradient is materialised
+            loss = self._frame.run(cam, gt, self.bg, factored=factored)
             from . import rasterizer as _r
             _r.last_num_rendered = self._frame.last_num_rendered
             if loss_host is not None:
@@ -209,7 +233,7 @@ class MeshTrainer:
             self._all_reduce()
             # gms_train_frame overwrites every gradient except the atomically accumulated vertex segment (group 0)
             if self.optimizer_step:
-                self.opt.step(zero_end=self.opt.ends[0])
+                self.opt.step(zero_end=self.opt.ends[0], sh=self._frame.sh_factors() if factored else None)
             else:
                 self.opt.zero_grad_partial(self.opt.ends[0])
             return loss

@@ -122,6 +122,9 @@ typedef struct gms_raster_grads {
     float* dL_dscales;        /* [P,3] */
     float* dL_drotations;     /* [P,4] */
     float* dL_dcov3D_precomp; /* [P,6] */
+    float* dL_dcolors_sh;     /* [P,3] optional, with shs: the clamp-masked colour gradient.  dL/dSH[k][c] = basis_k(dir) * this[c]
+                                 (rank 1 per camera), so with it dL_dshs may be NULL: 12 B instead of 192 B per Gaussian
+                                 (gms_adam_sh_factored consumes it) */
 } gms_raster_grads;
 
 /* ---- rasterizer ------------------------------------------------------------------------------- */
@@ -309,8 +312,35 @@ typedef struct gms_frame_args {
     int64_t* num_rendered;      /* host, optional (-1 on the sync-free path) */
     int64_t binning_capacity;   /* > 0: sync-free frame (gms_rasterize_forward_nosync semantics); 0: stock-style, one 4-byte D2H */
     uint32_t* n_host_mapped;    /* optional mapped pinned host [2]: N, overflow flag */
+    float* d_color_sh;          /* optional [3P + 3]: factored SH gradient (dL_dcolors_sh) followed by this frame's camera centre;
+                                   then d_features may be NULL and no SH gradient rows are written */
 } gms_frame_args;
 size_t gms_frame_workspace_bytes(int32_t P, int32_t W, int32_t H);
+/* Device pointers into a frame workspace (valid after gms_train_frame): this step's expansion outputs and images. */
+typedef struct gms_frame_view {
+    const float* xyz; const float* scales; const float* rotations; const float* opacities; const int32_t* radii;
+    const float* image; const float* invdepth;
+} gms_frame_view;
+int gms_frame_views(void* workspace, int32_t P, int32_t W, int32_t H, gms_frame_view* v);
+
+/* Adam step of the packed SH parameter [P,16,3] with its gradient rebuilt from FACTORS instead of read from memory:
+ *   dL/dSH_i[k][c] = grad_scale * sum_r basis_k(normalize(xyz_i - campos_r)) * dcolor_r[i][c],   r = 0..R-1
+ * `exchange` holds R slots of `slot_floats` floats, slot r = [3P colour gradients of frame r | its camera centre (3) | pad]
+ * (what gms_train_frame writes through d_color_sh).  Data parallel: the slots are all-gathered (12 B per Gaussian and
+ * rank instead of a 192 B reduce-scatter + all-gather), every rank runs this kernel on all Gaussians (replicated moments),
+ * so no parameter all-gather is needed either.  Learning rates / bias correction as in gms_adam_step (DC coefficient:
+ * lr_dc, the other 15: lr_rest; arguments_games/__init__.py:17-30). */
+typedef struct gms_adam_sh_args {
+    int32_t P, M, sh_degree, R;
+    const float* xyz;          /* [P,3] Gaussian centres of this step (gms_frame_views) */
+    const float* exchange;     /* [R, slot_floats] */
+    int64_t slot_floats;
+    float grad_scale;          /* 1/R */
+    float* p; float* m; float* v;
+    double lr_dc, lr_rest, beta1, beta2, eps;
+    int32_t step;
+} gms_adam_sh_args;
+int gms_adam_sh_factored(const gms_adam_sh_args* a, void* cuda_stream);
 int gms_train_frame(const gms_frame_args* a, gms_alloc_fn alloc, void* alloc_user, void* cuda_stream);
 
 /* ---- image sink / source ---------------------------------------- */

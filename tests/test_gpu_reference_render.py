@@ -176,3 +176,53 @@ def test_reference_animated_renderer_matches_oracle(ref, t):
     st, og = _oracle_chain(p, S, dC, (means3D, m.get_scaling, m.get_rotation), triangles=tri)
     og.pop("vertices")                      # the animated path feeds triangles directly: no gradient reaches pc.vertices
     _check_against_oracle(pkg, m, st, og, f"animated t={t}", GRAD_TOL)
+
+
+def test_checkpoint_written_here_loads_in_the_reference(ref, tmp_path):
+    """io_ply.save_mesh_model -> the reference's own GaussianMeshModel.load_ply (gaussian_mesh_model.py:211-225 ->
+    scene/gaussian_model.py:226-262) -> its render(): the same image as the model that was saved.  `plyfile` is absent from
+    the image; the reference's loader is served by a reader that implements the three things it uses
+    (PlyData.read, elements[0][name], elements[0].properties[i].name) on top of the PLY specification."""
+    import sys
+    import types as _t
+    from gms_b200 import io_ply
+    from gms_b200.model import MeshGaussianModel
+    from gms_b200.trainer import render_frame
+
+    class _El:
+        def __init__(self, data, names):
+            self.data, self.properties = data, [_t.SimpleNamespace(name=n) for n in names]
+
+        def __getitem__(self, k):
+            return self.data[k]
+
+    class _PlyData:
+        def __init__(self, elements):
+            self.elements = elements
+
+        @staticmethod
+        def read(path):
+            data, names = io_ply.read_ply_vertices(path)
+            return _PlyData([_El(data, names)])
+
+    import scene.gaussian_model as sgm
+    old = sgm.PlyData
+    sgm.PlyData = _PlyData
+    try:
+        p = scenes.init_mesh_gaussians(*scenes.icosphere(3), K=3, seed=31, trained_like=True)
+        ours = MeshGaussianModel.from_params(p, "cuda")
+        ply = str(tmp_path / "point_cloud" / "iteration_30000" / "point_cloud.ply")
+        io_ply.save_mesh_model(ply, ours)
+        m = ref.GaussianMeshModel(3)
+        m.load_ply(ply)
+        m.active_sh_degree = 3
+        assert m.vertices.is_cuda and m._alpha.is_cuda and m.faces.is_cuda          # used where they are: no .cuda() in the reference
+        m.update_alpha(); m.prepare_scaling_rot()
+        cam = scenes.look_at_camera((2.3, 0.9, 1.1), (0, 0, 0), 320, 240)
+        bg = torch.ones(3, device="cuda")
+        with torch.no_grad():
+            a = ref.render(_minicam(ref, cam), m, PIPE, bg)["render"]
+            b = render_frame(ours, cam.to("cuda"), bg, fused=False)[0]
+        assert float((a - b).abs().max()) <= 1e-5
+    finally:
+        sgm.PlyData = old
