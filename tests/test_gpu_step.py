@@ -195,3 +195,34 @@ def test_sync_free_native_frame_equals_synchronising_frame():
     assert int(fa.n_host[1]) == 1
     fa.run(cams[0], gts[0], bg); torch.cuda.synchronize()
     assert fa.overflows == 1 and int(fa.n_host[1]) == 0 and fa.last_num_rendered == na[0]
+
+
+def test_factored_sh_gradient_equals_dense_path():
+    """The native trainer hands the SH gradient over as factors (colour gradient x SH basis rebuilt inside k_adam_sh,
+    gms_adam_sh_factored) instead of 192 B/Gaussian of rows: same parameters as the dense path (gradient rows written by
+    k_preprocess_bwd, read by k_adam) after a few steps, for every active SH degree."""
+    for degree in (3, 1, 0):
+        p = scenes.init_mesh_gaussians(*scenes.icosphere(4), K=3, seed=9)
+        cams = [c.to("cuda") for c in scenes.ring_cameras(4, 2.5, 352, 256)]
+        bg = torch.ones(3, device="cuda")
+        gt_model = MeshGaussianModel.from_params(scenes.init_mesh_gaussians(*scenes.icosphere(4), K=3, seed=80), "cuda")
+        with torch.no_grad():
+            gts = [render_frame(gt_model, c, bg)[0].clamp(0, 1).contiguous() for c in cams]
+        out = []
+        for factored in (True, False):
+            m = MeshGaussianModel.from_params(p, "cuda", packed_features=True, active_sh_degree=degree)
+            tr = MeshTrainer(m, bg, fast=True, native=True, sh_factored=factored)
+            losses_ = [tr.step(cams[s % 4], gts[s % 4]).item() for s in range(5)]
+            assert tr.sh_factored == factored
+            out.append((losses_, m._features.detach().clone(), m._opacity.detach().clone(), m._alpha.detach().clone()))
+        (la, fa, oa, aa), (lb, fb, ob, ab) = out
+        np.testing.assert_allclose(la, lb, rtol=1e-5)
+        assert la[-1] < la[0]
+        ref = float(fb.abs().max())
+        assert float((fa - fb).abs().max()) <= 2e-5 * ref, (degree, float((fa - fb).abs().max()), ref)
+        np.testing.assert_allclose(oa.cpu().numpy(), ob.cpu().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(aa.cpu().numpy(), ab.cpu().numpy(), rtol=1e-4, atol=1e-5)
+        if degree < 3:      # coefficients above the active degree get a zero gradient: untouched by either path
+            nc = (degree + 1) ** 2
+            init = torch.cat((p._features_dc, p._features_rest), 1).cuda()
+            assert torch.equal(fa[:, nc:], init[:, nc:]) and torch.equal(fb[:, nc:], init[:, nc:])
