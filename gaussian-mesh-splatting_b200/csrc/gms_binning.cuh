@@ -16,8 +16,9 @@
 //            point_list[base[tile] + row[tile]++] = Gaussian id  with the batches COMMITTING IN DEPTH ORDER: a warp
 //            prepares its batch on its own (loads two batches ahead, a warp scan numbers the batch's (Gaussian, tile) pairs
 //            Gaussian-major, every step hands 32 consecutive pairs to the 32 lanes, lanes of a step that hit the same tile
-//            are ranked with match.any), then waits for its turn and draws the slots with one shared-memory atomic per
-//            distinct tile and step.  Only those atomics are serialised; 2 CTAs x 16 warps per SM keep the rest overlapped.
+//            are ranked with match.any), then waits for its turn (named barriers chain the warps: bar.arrive / bar.sync,
+//            no spinning) and draws the slots with one shared-memory atomic per distinct tile and step.  Only those
+//            atomics are serialised; 2 CTAs x 16 warps per SM keep everything else overlapped.
 //
 // The result is bit-identical to the stock (tile << 32 | depth) sort (tests/test_gpu_parity.py).  Device-side N, no host
 // synchronisation, no scan over P, no key arrays.  Grid = 2 CTAs per SM (cooperative launch, grid.sync between the phases).
@@ -49,6 +50,10 @@ constexpr int GMS_BIN_STEPS = 8;            // steps (of 32 pairs) prepared ahea
 // dynamic shared memory: one row of T 32-bit counters + T 32-bit bases
 static inline size_t gms_bin_smem_bytes(int T) { return 2 * (size_t)T * sizeof(uint32_t) + 64; }
 
+// named barriers 1..15 hand the "turn" from the warp that commits batch b to the one that commits batch b + 1
+__device__ __forceinline__ void gms_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void gms_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+
 __device__ __forceinline__ void gms_bin_unpack(const uint2 r, int gx, int& t00, int& w, int& nt) {
     const int x0 = (int)(r.x & 0xffffu), y0 = (int)(r.x >> 16);
     w = (int)(r.y & 0xffffu) - x0;
@@ -62,7 +67,6 @@ __global__ void __launch_bounds__(GMS_BIN_THREADS, 2) k_bin_tiles(GmsBinArgs a) 
     __shared__ uint32_t s_part[GMS_BIN_THREADS];
     __shared__ uint32_t s_grp[GMS_BIN_THREADS / 32][64];
     __shared__ uint32_t s_n;
-    __shared__ volatile uint32_t s_turn;
     cg::grid_group grid = cg::this_grid();
     constexpr int W = GMS_BIN_THREADS / 32;
     const unsigned FULL = 0xffffffffu;
@@ -72,7 +76,6 @@ __global__ void __launch_bounds__(GMS_BIN_THREADS, 2) k_bin_tiles(GmsBinArgs a) 
     uint32_t* row = bin_smem;               // [T] this CTA's running count per tile
     uint32_t* base = bin_smem + T;          // [T] first list position of this CTA's entries per tile
     for (int i = threadIdx.x; i < T; i += GMS_BIN_THREADS) row[i] = 0;
-    if (threadIdx.x == 0) s_turn = 0;
     // slice of the depth order owned by this CTA, in batches of 32 Gaussians dealt round-robin to the warps
     const uint32_t nvis = min(*a.nvis, (uint32_t)a.P);
     const uint32_t per = ((nvis + G - 1) / G + 31u) & ~31u;
@@ -256,28 +259,30 @@ __global__ void __launch_bounds__(GMS_BIN_THREADS, 2) k_bin_tiles(GmsBinArgs a) 
                     const uint32_t peers = __match_any_sync(FULL, active ? (uint32_t)t : (0x40000000u | (uint32_t)lane));
                     meta[s] = (uint32_t)(__ffs(peers) - 1) | ((uint32_t)__popc(peers & lt) << 8) | ((uint32_t)__popc(peers) << 16);
                 }
-                if (!mine) {
-                    while (s_turn != b) __nanosleep(32);
-                    __syncwarp();
+                if (!mine) {        // wait for batch b - 1 to have drawn its slots (named barrier: no spinning, ~tens of cycles)
+                    if (b > 0) gms_bar_sync(1 + (int)((b - 1) % 15u), 64);
                     mine = true;
                 }
+                uint32_t old[GMS_BIN_STEPS];
+#pragma unroll
+                for (int s = 0; s < GMS_BIN_STEPS; s++) {       // the ordered section: nothing but the atomics, back to back
+                    old[s] = 0;
+                    if (tt[s] >= 0 && lane == (int)(meta[s] & 0xffu)) old[s] = atomicAdd(&row[tt[s]], meta[s] >> 16);
+                }
+#pragma unroll
+                for (int s = 0; s < GMS_BIN_STEPS; s++) old[s] = __shfl_sync(FULL, old[s], (int)(meta[s] & 0xffu));   // (consumes the results: the atomics have been performed)
+                const bool last_chunk = p0 + 32 * GMS_BIN_STEPS >= tot;
+                if (last_chunk && b + 1 < nbatch) gms_bar_arrive(1 + (int)(b % 15u), 64);       // hand the turn to batch b + 1
 #pragma unroll
                 for (int s = 0; s < GMS_BIN_STEPS; s++) {
-                    if (p0 + 32 * s >= tot) break;          // uniform
-                    const int leader = (int)(meta[s] & 0xffu);
-                    uint32_t old = 0;
-                    if (tt[s] >= 0 && lane == leader) old = atomicAdd(&row[tt[s]], meta[s] >> 16);
-                    old = __shfl_sync(FULL, old, leader);
                     if (tt[s] >= 0) {
-                        const uint32_t pos = base[tt[s]] + old + ((meta[s] >> 8) & 0xffu);
+                        const uint32_t pos = base[tt[s]] + old[s] + ((meta[s] >> 8) & 0xffu);
                         a.point_list[pos] = gg[s];
                         if (a.tile_keys) a.tile_keys[pos] = (uint32_t)tt[s];
                     }
                 }
-                if (p0 + 32 * GMS_BIN_STEPS >= tot) break;
+                if (last_chunk) break;
             }
-            __syncwarp();
-            if (lane == 0) { __threadfence_block(); s_turn = b + 1; }
         }
     }
 }

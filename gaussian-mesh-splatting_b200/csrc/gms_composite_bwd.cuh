@@ -48,7 +48,8 @@ __device__ __forceinline__ void gms_red_flush(const float* red, float (*part)[12
 
 // DEPTH = false: no loss on the inverse-depth image (train.py never puts one): the depth channel of the recurrence and its
 // moment sum are compiled out.
-template <int MINB, bool DEPTH>
+// GRP = 3: a panel group's three alpha evaluations are issued ahead of the serial recurrence; GRP = 1: one splat at a time.
+template <int MINB, bool DEPTH, int GRP = 3>
 __global__ void __launch_bounds__(GMS_CB, MINB)
 k_composite_bwd5(const int2* __restrict__ ranges, const int* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
                  const float4* __restrict__ recs, int W, int H, int gx, const float* __restrict__ bg,
@@ -111,6 +112,7 @@ k_composite_bwd5(const int2* __restrict__ ranges, const int* __restrict__ tile_o
         if (k < cnt) { pos_cur = (int)ql[k]; id_cur = (int)plist[pos_cur]; ra = recs[3 * id_cur]; rb = recs[3 * id_cur + 1]; rc = recs[3 * id_cur + 2]; }
         if (nb >= 2) { pos_nx = (int)ql[(nb - 2) * GMS_WB + lane]; id_nx = (int)plist[pos_nx]; }
     }
+    if (GRP == 3) {
     for (int b = nb - 1; b >= 0; b--) {
         S.id[lane] = id_cur; S.pos[lane] = pos_cur;
         if (id_cur >= 0) gms_slab3_store(reinterpret_cast<GmsSlab3&>(S), lane, ra, rb, rc);
@@ -212,6 +214,93 @@ k_composite_bwd5(const int2* __restrict__ ranges, const int* __restrict__ tile_o
             atomicAdd(reinterpret_cast<float2*>(&dgeom[3 * id + 2]), s2);   // dL/drgb.b, dL/dinvdepth
         }
         __syncwarp();
+    }
+    } else {
+    for (int b = nb - 1; b >= 0; b--) {
+        S.id[lane] = id_cur; S.pos[lane] = pos_cur;
+        if (id_cur >= 0) gms_slab3_store(reinterpret_cast<GmsSlab3&>(S), lane, ra, rb, rc);
+        uint32_t m = __ballot_sync(0xffffffffu, id_cur >= 0);
+        id_cur = id_nx; pos_cur = pos_nx;
+        if (id_cur >= 0) { ra = recs[3 * id_cur]; rb = recs[3 * id_cur + 1]; rc = recs[3 * id_cur + 2]; }
+        if (b >= 2) { pos_nx = (int)ql[(b - 2) * GMS_WB + lane]; id_nx = (int)plist[pos_nx]; } else { pos_nx = -1; id_nx = -1; }
+        __syncwarp();
+        const uint32_t touched_all = m;
+        uint32_t touched = 0;
+        while (m) {
+            const int j = 31 - __clz(m);
+            m &= ~(1u << j);
+            const int pos = S.pos[j];
+            const float4 Q0 = S.q0[j], Q1 = S.q1[j], Q2 = S.q2[j];
+            f2 dx, dy;
+            const f2 power = gms_power2(Q0, Q1, Q2, npx, npy, dx, dy);
+            const f2 sc = f2mul(power, make_float2(GMS_LOG2E, GMS_LOG2E));
+            const f2 G = make_float2(gms_ex2(sc.x), gms_ex2(sc.y));
+            const f2 araw = f2mul(make_float2(Q2.z, Q2.w), G);
+            const float a0 = fminf(GMS_ALPHA_MAX, araw.x), a1 = fminf(GMS_ALPHA_MAX, araw.y);
+            const bool v0 = pos < lastA && power.x <= 0.0f && a0 >= GMS_ALPHA_MIN;
+            const bool v1 = pos < lastB && power.y <= 0.0f && a1 >= GMS_ALPHA_MIN;
+            const float4 Q3 = S.q3[j], Q4 = S.q4[j];
+            const f2 alpha = make_float2(v0 ? a0 : 0.f, v1 ? a1 : 0.f);
+            const f2 oma = f2fma(alpha, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+            const f2 inv = make_float2(gms_rcp(oma.x), gms_rcp(oma.y));
+            T = f2mul(T, inv);
+            const f2 w = f2mul(alpha, T);
+            const f2 cr = make_float2(Q3.x, Q3.y), cg = make_float2(Q3.z, Q3.w), cb = make_float2(Q4.x, Q4.y), cd = make_float2(Q4.z, Q4.w);
+            const f2 neg1 = make_float2(-1.f, -1.f);
+            // dL/dalpha = sum_c (c - B_c) * dL/dC_c   (then * T, + background term)
+            f2 dLa = f2mul(f2fma(Br, neg1, cr), dpr);
+            dLa = f2fma(f2fma(Bg, neg1, cg), dpg, dLa);
+            dLa = f2fma(f2fma(Bb, neg1, cb), dpb, dLa);
+            if (DEPTH) dLa = f2fma(f2fma(Bd, neg1, cd), dpd, dLa);
+            // advance "behind": B <- alpha*c + (1-alpha)*B
+            Br = f2fma(alpha, cr, f2mul(oma, Br)); Bg = f2fma(alpha, cg, f2mul(oma, Bg));
+            Bb = f2fma(alpha, cb, f2mul(oma, Bb));
+            if (DEPTH) Bd = f2fma(alpha, cd, f2mul(oma, Bd));
+            dLa = f2mul(dLa, T);
+            dLa = f2fma(f2mul(nTfin, inv), bgdot, dLa);
+            f2 q = f2mul(dLa, G);
+            q.x = v0 ? q.x : 0.f; q.y = v1 ? q.y : 0.f;
+            const f2 qx = f2mul(q, dx), qy = f2mul(q, dy);
+            const f2 pxx = f2mul(qx, dx), pxy = f2mul(qx, dy), pyy = f2mul(qy, dy);
+            const f2 wr = f2mul(w, dpr), wg = f2mul(w, dpg), wb = f2mul(w, dpb);
+            const f2 wd = DEPTH ? f2mul(w, dpd) : make_float2(0.f, 0.f);
+            float v[10];
+            v[0] = qx.x + qx.y; v[1] = qy.x + qy.y; v[2] = pxx.x + pxx.y; v[3] = pxy.x + pxy.y; v[4] = pyy.x + pyy.y;
+            v[5] = q.x + q.y; v[6] = wr.x + wr.y; v[7] = wg.x + wg.y; v[8] = wb.x + wb.y; v[9] = wd.x + wd.y;
+            {
+                float* col = red + (pend * NV) * GMS_RED_STRIDE + lane;
+#pragma unroll
+                for (int i = 0; i < NV; i++) col[i * GMS_RED_STRIDE] = v[i];
+                pj |= j << (8 * pend);
+                if (++pend == 3) { gms_red_flush<NV>(red, S.part, pj, 3 * NV, lane, rk8, ri); pend = 0; pj = 0; }
+            }
+            touched |= 1u << j;
+        }
+        touched = touched_all;
+        if (pend) { gms_red_flush<NV>(red, S.part, pj, pend * NV, lane, rk8, ri); pend = 0; pj = 0; }
+        __syncwarp();
+        if ((touched >> lane) & 1u) {
+            const int id = S.id[lane];
+            const float4 s0 = *reinterpret_cast<const float4*>(&S.part[lane][0]);
+            const float4 s1 = *reinterpret_cast<const float4*>(&S.part[lane][4]);
+            float2 s2 = *reinterpret_cast<const float2*>(&S.part[lane][8]);
+            if (!DEPTH) s2.y = 0.f;                 // the 9-value panel never writes the inverse-depth sum
+            const float4 Q1 = S.q1[lane], Q2 = S.q2[lane];
+            const float conx = Q1.x, ncony = Q1.z, conz = Q2.x, op = Q2.z;
+            float4 g0, g1;
+            g0.x = (-conx * s0.x + ncony * s0.y) * op * halfW;  // dL/dmean2D.x (NDC-scaled)
+            g0.y = (-conz * s0.y + ncony * s0.x) * op * halfH;  // dL/dmean2D.y
+            g0.z = -0.5f * op * s0.z;                           // dL/dconic.x
+            g0.w = -0.5f * op * s0.w;                           // dL/dconic.y (stock half convention)
+            g1.x = -0.5f * op * s1.x;                           // dL/dconic.z
+            g1.y = s1.y;                                        // dL/d(conic_opacity.w)
+            g1.z = s1.z; g1.w = s1.w;                           // dL/drgb.r, .g
+            atomicAdd(&dgeom[3 * id], g0);
+            atomicAdd(&dgeom[3 * id + 1], g1);
+            atomicAdd(reinterpret_cast<float2*>(&dgeom[3 * id + 2]), s2);   // dL/drgb.b, dL/dinvdepth
+        }
+        __syncwarp();
+    }
     }
 }
 

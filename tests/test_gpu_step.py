@@ -145,14 +145,15 @@ def test_native_frame_equals_autograd_path():
     from gms_b200.trainer import NativeFrame
     fr = NativeFrame(ma, 352, 256)
     la = fr.run(cams[0], gts[0], bg).item()
-    ga = ta.opt.flat_grad.clone(); ta.opt.zero_grad()
+    ga = [q.grad.clone() for q in ma.parameters()]; ta.opt.zero_grad()       # (the two optimisers order their flat buffers differently)
     from gms_b200 import rasterizer
     rasterizer.DIRECT_SH_GRAD = True
     image, _, _ = render_frame(mb, cams[0], bg)
     lb = losses.fused_training_loss(image, gts[0], 0.2); lb.backward()
-    gb = tb.opt.flat_grad.clone(); tb.opt.zero_grad()
+    gb = [q.grad.clone() for q in mb.parameters()]; tb.opt.zero_grad()
     assert abs(la - lb.item()) <= 1e-6 * max(1.0, abs(lb.item()))
-    assert (ga - gb).abs().max().item() <= 2e-3 * gb.abs().max().item()
+    for x, y in zip(ga, gb):
+        assert (x - y).abs().max().item() <= 2e-3 * y.abs().max().item()
     # a few full steps
     ta = MeshTrainer(ma, bg, fast=True, native=True); tb = MeshTrainer(mb, bg, fast=True, native=False)
     for s in range(4):
