@@ -44,13 +44,14 @@ struct GmsBinArgs {
     volatile uint32_t* n_host;  // mapped pinned host [2] or NULL: N, overflow flag (readable without a sync once the kernel ran)
 };
 
-constexpr int GMS_BIN_THREADS = 512;        // 16 warps per CTA
+constexpr int GMS_BIN_THREADS = 384;        // 12 warps per CTA (<= 15: one named barrier per warp hands the turn on)
 constexpr int GMS_BIN_STEPS = 8;            // steps (of 32 pairs) prepared ahead of the ordered section
 
 // dynamic shared memory: one row of T 32-bit counters + T 32-bit bases
 static inline size_t gms_bin_smem_bytes(int T) { return 2 * (size_t)T * sizeof(uint32_t) + 64; }
 
-// named barriers 1..15 hand the "turn" from the warp that commits batch b to the one that commits batch b + 1
+// named barriers 1..W hand the "turn" from the warp that commits batch b to the one that commits batch b + 1 (barrier 1 + w
+// is only ever waited on by warp w and arrived on by warp w - 1, so at most one hand-over is pending per barrier)
 __device__ __forceinline__ void gms_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void gms_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(GMS_BIN_THREADS, 2) k_bin_tiles(GmsBinArgs a) 
                     meta[s] = (uint32_t)(__ffs(peers) - 1) | ((uint32_t)__popc(peers & lt) << 8) | ((uint32_t)__popc(peers) << 16);
                 }
                 if (!mine) {        // wait for batch b - 1 to have drawn its slots (named barrier: no spinning, ~tens of cycles)
-                    if (b > 0) gms_bar_sync(1 + (int)((b - 1) % 15u), 64);
+                    if (b > 0) gms_bar_sync(1 + warp, 64);          // barrier (1 + w) belongs to the RECEIVING warp w: only warp w - 1 arrives on it
                     mine = true;
                 }
                 uint32_t old[GMS_BIN_STEPS];
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(GMS_BIN_THREADS, 2) k_bin_tiles(GmsBinArgs a) 
 #pragma unroll
                 for (int s = 0; s < GMS_BIN_STEPS; s++) old[s] = __shfl_sync(FULL, old[s], (int)(meta[s] & 0xffu));   // (consumes the results: the atomics have been performed)
                 const bool last_chunk = p0 + 32 * GMS_BIN_STEPS >= tot;
-                if (last_chunk && b + 1 < nbatch) gms_bar_arrive(1 + (int)(b % 15u), 64);       // hand the turn to batch b + 1
+                if (last_chunk && b + 1 < nbatch) gms_bar_arrive(1 + (warp + 1) % W, 64);      // hand the turn to batch b + 1 (warp w + 1)
 #pragma unroll
                 for (int s = 0; s < GMS_BIN_STEPS; s++) {
                     if (tt[s] >= 0) {

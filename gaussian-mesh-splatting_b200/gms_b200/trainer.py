@@ -157,7 +157,7 @@ class NativeFrame:
         if self.sync_free and not first:
             if int(self.n_host[1]) != 0:       # some earlier frame overflowed the binning region: grow before this one
                 self.overflows += 1
-                self.capacity = int(max(self.capacity, int(self.n_host[0])) * 1.5) + (1 << 20)
+                self.capacity = int(max(self.capacity, int(self.n_host[0])) * 1.25) + (1 << 18)
                 self.n_host[1] = 0
             a.binning_capacity, a.n_host_mapped = self.capacity, self.n_host.data_ptr()
         with torch.cuda.device(self.dev):
@@ -165,7 +165,7 @@ class NativeFrame:
                        "gms_train_frame")
         if self.sync_free and first:           # the one synchronising frame told us N
             n = max(int(self.n_rendered.value), 0)
-            self.capacity = int(n * 1.5) + (1 << 20)
+            self.capacity = int(n * 1.25) + (1 << 18)      # the tile sort runs over the capacity: keep the slack modest
             self.n_host[0] = n
         return self.loss[0]
 

@@ -175,13 +175,24 @@ def test_binning_implementations_give_the_stock_order(bin_impl, sort_impl, P, W,
     assert_forward_parity(st, color, radii, invd, state)
 
 
-def test_nosync_forward_matches_and_overflow_degrades_to_background():
+@pytest.mark.parametrize("bin_impl", [0, 1])
+def test_nosync_forward_matches_and_overflow_degrades_to_background(bin_impl):
     """gms_rasterize_forward_nosync through the raw C ABI: with enough capacity it equals the synchronising call bit for
     bit and reports N through the mapped host word; with too little it raises the overflow flag and renders the
     background (never writes past the region)."""
     import ctypes as C
     from gms_b200 import rasterizer as R
     S, g = _case(20000, 400, 300, seed=9)
+    old_bin = _lib.set_option("bin_impl", bin_impl)
+    try:
+        _nosync_body(S, g, bin_impl)
+    finally:
+        _lib.set_option("bin_impl", old_bin)
+
+
+def _nosync_body(S, g, bin_impl):
+    import ctypes as C
+    from gms_b200 import rasterizer as R
     color, radii, invd, state, _ = run_gpu(S, g)
     N = state["num_rendered"]
     dev = torch.device("cuda")
@@ -211,7 +222,7 @@ def test_nosync_forward_matches_and_overflow_degrades_to_background():
         _lib.check(_lib.lib().gms_rasterize_forward_nosync(C.byref(s), C.byref(i), C.byref(o), cb, None, C.byref(saved), cap,
                                                            n_host.data_ptr(), torch.cuda.current_stream().cuda_stream), "nosync")
         torch.cuda.synchronize()
-        assert int(saved.num_rendered) == -1 and int(saved.flags) & 1 and int(saved.binning_capacity) == cap
+        assert int(saved.num_rendered) == -1 and (int(saved.flags) & 1) == bin_impl and int(saved.binning_capacity) == cap
         assert int(n_host[0]) == N and int(n_host[1]) == int(expect_overflow)
         for which, nb in guard.items():
             assert bool((bufs[which][nb:] == 0xAB).all()), f"scratch region {which} overrun"
