@@ -306,7 +306,7 @@ def run_render_animated(args, params, cams, dims, dev, world, rank, local):
     if args.save_images:
         from gms_b200 import io_image
         os.makedirs(args.save_images, exist_ok=True)
-        sink = io_image.ImageSink(H, W, fmt=args.image_format, slots=6, workers=4, device=dev,
+        sink = io_image.ImageSink(H, W, fmt=args.image_format, device=dev,
                                   raw_path=os.path.join(args.save_images, f"rank{rank}.rgb") if args.image_format == "raw" else None)
 
     def frame(i):
@@ -749,8 +749,8 @@ def main():
                 ab += 12 * (world - 1) * P          # replicated factored optimizer: one more 12 B colour gradient per extra rank
             per_kernel[name] = {"ms": ms / cnt, "launches_per_step": cnt / min(K_, 10), "algo_bytes": ab,
                                 "gbs": (ab / (ms / cnt * 1e-3) / 1e9) if ms > 0 else None}
-    if "cub_sort_tiles" in per_kernel and not any(o.startswith("bin_impl=0") for o in args.opt):
-        per_kernel["bin_tiles"] = per_kernel.pop("cub_sort_tiles")      # default build: the cooperative counting kernel runs in that slot
+    if "cub_sort_tiles" in per_kernel and any(o.startswith("bin_impl=1") for o in args.opt):
+        per_kernel["bin_tiles"] = per_kernel.pop("cub_sort_tiles")      # --opt bin_impl=1: the cooperative counting kernel runs in that slot
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"] * per_kernel[k]["launches_per_step"]) if per_kernel else None
     peak, peak_src = measured_peak_gbs()
     roof = None

@@ -147,8 +147,12 @@ class ImageSink:
         sink.close()                                                              # waits for the files
     """
 
-    def __init__(self, height: int, width: int, fmt: str = "png", channels: int = 3, slots: int = 4, workers: int = 2,
+    def __init__(self, height: int, width: int, fmt: str = "png", channels: int = 3, slots: Optional[int] = None, workers: Optional[int] = None,
                  compress_level: int = 1, device="cuda", raw_path: Optional[str] = None):
+        if workers is None:     # deflate is the slow part of a PNG (zlib releases the GIL): spread it over the host cores
+            workers = max(2, min(16, (os.cpu_count() or 4) // 4)) if fmt == "png" else 2
+        if slots is None:
+            slots = workers + 2
         if fmt not in ("png", "ppm", "raw"):
             raise ValueError("fmt must be 'png', 'ppm' or 'raw'")
         self.H, self.W, self.C, self.fmt, self.level = int(height), int(width), int(channels), fmt, int(compress_level)
