@@ -532,6 +532,33 @@ def run_comparators(model, cams_dev, gts, bg, dims, dev, n_frames=12):
         importlib.reload(rgr)
     except Exception as e:  # pragma: no cover
         out["expansion_error"] = repr(e)
+
+    # (4) image sink vs torchvision.utils.save_image (scripts/render_time_animated.py:86-87), frames per second incl. the files
+    try:
+        import shutil
+        import tempfile
+        import torchvision.utils as tvu
+        from gms_b200 import io_image
+        frames = [g.clamp(0, 1) for g in gts[:8]]
+        tmp = tempfile.mkdtemp(prefix="gms_sink_")
+        res = {}
+        t0 = time.perf_counter()
+        for k in range(8):
+            tvu.save_image(frames[k % len(frames)], os.path.join(tmp, f"ref_{k}.png"))
+        torch.cuda.synchronize()
+        res["torchvision_save_image_png_ms"] = (time.perf_counter() - t0) / 8 * 1e3
+        for fmt in ("png", "ppm", "raw"):
+            n = 48
+            t0 = time.perf_counter()
+            with io_image.ImageSink(H, W, fmt=fmt, device=dev, raw_path=os.path.join(tmp, "frames.rgb") if fmt == "raw" else None) as sink:
+                for k in range(n):
+                    sink.write(frames[k % len(frames)], os.path.join(tmp, f"ours_{k}.{fmt}"))
+            res[f"image_sink_{fmt}_ms"] = (time.perf_counter() - t0) / n * 1e3
+        shutil.rmtree(tmp, ignore_errors=True)
+        res["what"] = "host wall-clock per 1080p frame incl. the file write (tmp dir); the sink overlaps it with rendering, save_image blocks the loop"
+        out["image_sink"] = res
+    except Exception as e:  # pragma: no cover
+        out["image_sink_error"] = repr(e)
     return out
 
 

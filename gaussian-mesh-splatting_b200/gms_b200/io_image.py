@@ -134,7 +134,8 @@ def load_image_u8(path: str) -> torch.Tensor:
         arr = np.frombuffer(parts[4][:W * H * 3], np.uint8).reshape(H, W, 3)
     else:
         raise ValueError(f"{path}: unsupported image format")
-    return torch.from_numpy(np.ascontiguousarray(arr)).pin_memory() if torch.cuda.is_available() else torch.from_numpy(np.ascontiguousarray(arr))
+    t = torch.from_numpy(np.array(arr, dtype=np.uint8, order="C"))      # (owning, writable copy)
+    return t.pin_memory() if torch.cuda.is_available() else t
 
 
 class ImageSink:
