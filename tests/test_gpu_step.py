@@ -195,7 +195,8 @@ def test_sync_free_native_frame_equals_synchronising_frame():
     fa.run(cams[0], gts[0], bg); torch.cuda.synchronize()
     assert int(fa.n_host[1]) == 1
     fa.run(cams[0], gts[0], bg); torch.cuda.synchronize()
-    assert fa.overflows == 1 and int(fa.n_host[1]) == 0 and fa.last_num_rendered == na[0]
+    assert fa.overflows == 1 and int(fa.n_host[1]) == 0 and fa.capacity >= fa.last_num_rendered > 0
+    assert abs(fa.last_num_rendered - na[0]) <= 0.05 * na[0]        # (same camera; the parameters moved by seven Adam steps)
 
 
 def test_factored_sh_gradient_equals_dense_path():
