@@ -58,6 +58,7 @@ class FlatAdam:
             self.ends.append(off)
         self.betas, self.eps, self.t = betas, eps, 0
         self._kernel = kernel or self._cuda_kernel       # `kernel`: test hook (a callable taking the _adam_desc dict)
+        self._comm = None                                # side stream of the factored exchange (created on first use)
 
     @property
     def flat_grad(self) -> torch.Tensor:
@@ -117,16 +118,32 @@ class FlatAdam:
         import torch.distributed as dist
         prefix = self.ends[-2]                       # everything but the SH group
         ex = sh["exchange"]
+        gathered = None
         if self.world > 1:
+            dev = self.p.device
+            main = torch.cuda.current_stream(dev)
+            # The colour gradients are final right after the preprocess backward (event recorded inside gms_train_frame): their
+            # all-gather is issued from a side stream so that it runs while the opacity / expansion backward finish; the
+            # all-reduce of the other gradients follows on the main stream; k_adam_sh waits for the gather only.
+            if sh.get("event") is not None:
+                if self._comm is None:
+                    self._comm = torch.cuda.Stream(dev)
+                self._comm.wait_event(sh["event"])
+                with torch.cuda.stream(self._comm):
+                    dist.all_gather_into_tensor(ex.view(-1), ex[self.rank])
+                    gathered = self._comm.record_event()
             if dist.get_backend() == "nccl":
                 dist.all_reduce(self.g[:prefix], op=dist.ReduceOp.AVG)
             else:
                 dist.all_reduce(self.g[:prefix], op=dist.ReduceOp.SUM); self.g[:prefix].mul_(1.0 / self.world)
-            dist.all_gather_into_tensor(ex.view(-1), ex[self.rank])
+            if gathered is None:
+                dist.all_gather_into_tensor(ex.view(-1), ex[self.rank])
         d = self._adam_desc(prefix, 0, self.p, self.g, 1 if zero_end is None else 2, 0 if zero_end is None else zero_end)
         for k in ("seg_end", "lr0", "lr1", "inner", "period"):
             d[k] = d[k][:-1]
         self._kernel(d)
+        if gathered is not None:
+            torch.cuda.current_stream(self.p.device).wait_event(gathered)
         gsh = self.groups[-1]
         f = gsh["param"]
         off = self.ends[-2]

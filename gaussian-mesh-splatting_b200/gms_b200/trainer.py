@@ -79,6 +79,8 @@ class NativeFrame:
         self.world, self.rank = int(world), int(rank)
         self.slot = (3 * P + 3 + 63) // 64 * 64
         self.exchange = None
+        self.ev_sh = None           # recorded by gms_train_frame right after the preprocess backward (world > 1: the exchange of the
+                                    # colour gradients starts there, on the optimizer's communication stream)
         self._check_model()
         scratch = {}
         self._scratch = scratch
@@ -121,7 +123,7 @@ class NativeFrame:
         from . import _lib
         v = _lib.FrameView()
         _lib.check(_lib.lib().gms_frame_views(self.ws.data_ptr(), self.model._scale.shape[0], self.W, self.H, C.byref(v)), "gms_frame_views")
-        return dict(xyz=v.xyz, exchange=self.exchange, degree=self.model.active_sh_degree)
+        return dict(xyz=v.xyz, exchange=self.exchange, degree=self.model.active_sh_degree, event=self.ev_sh)
 
     def run(self, cam: Camera, gt: torch.Tensor, bg: torch.Tensor, factored: bool = False) -> torch.Tensor:
         import ctypes as C
@@ -145,6 +147,11 @@ class NativeFrame:
             if self.exchange is None:
                 self.exchange = torch.zeros(self.world, self.slot, dtype=torch.float32, device=self.dev)
             a.d_features, a.d_color_sh = None, self.exchange[self.rank].data_ptr()
+            if self.world > 1:
+                if self.ev_sh is None:
+                    self.ev_sh = torch.cuda.Event()
+                    self.ev_sh.record(torch.cuda.current_stream(self.dev))      # (creates the underlying cudaEvent_t)
+                a.event_sh_ready = self.ev_sh.cuda_event
         s = a.settings
         s.image_height, s.image_width, s.tanfovx, s.tanfovy = self.H, self.W, cam.tanfovx, cam.tanfovy
         s.bg, s.scale_modifier = bg.data_ptr(), 1.0

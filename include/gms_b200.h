@@ -314,6 +314,9 @@ typedef struct gms_frame_args {
     uint32_t* n_host_mapped;    /* optional mapped pinned host [2]: N, overflow flag */
     float* d_color_sh;          /* optional [3P + 3]: factored SH gradient (dL_dcolors_sh) followed by this frame's camera centre;
                                    then d_features may be NULL and no SH gradient rows are written */
+    void* event_sh_ready;       /* optional cudaEvent_t recorded right after the preprocess backward: d_color_sh (or d_features) is
+                                   final from there on, so a data-parallel caller can start exchanging it on another stream while the
+                                   opacity / expansion backward still runs */
 } gms_frame_args;
 size_t gms_frame_workspace_bytes(int32_t P, int32_t W, int32_t H);
 /* Device pointers into a frame workspace (valid after gms_train_frame): this step's expansion outputs and images. */
