@@ -118,32 +118,49 @@ class FlatAdam:
         import torch.distributed as dist
         prefix = self.ends[-2]                       # everything but the SH group
         ex = sh["exchange"]
-        gathered = None
+        gathered = reduced = None
         if self.world > 1:
             dev = self.p.device
             main = torch.cuda.current_stream(dev)
-            # The colour gradients are final right after the preprocess backward (event recorded inside gms_train_frame): their
-            # all-gather is issued from a side stream so that it runs while the opacity / expansion backward finish; the
-            # all-reduce of the other gradients follows on the main stream; k_adam_sh waits for the gather only.
-            if sh.get("event") is not None:
+            avg = dist.get_backend() == "nccl"
+
+            def reduce_rest():
+                if avg:
+                    dist.all_reduce(self.g[:prefix], op=dist.ReduceOp.AVG)
+                else:
+                    dist.all_reduce(self.g[:prefix], op=dist.ReduceOp.SUM); self.g[:prefix].mul_(1.0 / self.world)
+
+            if self.g.is_cuda:
+                # Both collectives run from a side stream: the all-gather of the colour gradients starts right after the
+                # preprocess backward (event recorded inside gms_train_frame) and overlaps the opacity / expansion backward; the
+                # all-reduce of the other gradients starts when the frame is complete and overlaps k_adam_sh, which needs the
+                # gather only.  k_adam (the non-SH parameters) waits for the all-reduce.
                 if self._comm is None:
                     self._comm = torch.cuda.Stream(dev)
-                self._comm.wait_event(sh["event"])
-                with torch.cuda.stream(self._comm):
+                comm = self._comm
+                comm.wait_event(sh["event"] if sh.get("event") is not None else main.record_event())
+                with torch.cuda.stream(comm):
                     dist.all_gather_into_tensor(ex.view(-1), ex[self.rank])
-                    gathered = self._comm.record_event()
-            if dist.get_backend() == "nccl":
-                dist.all_reduce(self.g[:prefix], op=dist.ReduceOp.AVG)
+                    gathered = comm.record_event()
+                comm.wait_event(main.record_event())
+                with torch.cuda.stream(comm):
+                    reduce_rest()
+                    reduced = comm.record_event()
             else:
-                dist.all_reduce(self.g[:prefix], op=dist.ReduceOp.SUM); self.g[:prefix].mul_(1.0 / self.world)
-            if gathered is None:
                 dist.all_gather_into_tensor(ex.view(-1), ex[self.rank])
+                reduce_rest()
+        if gathered is not None:
+            torch.cuda.current_stream(self.p.device).wait_event(gathered)
+        self._adam_sh(sh)
+        if reduced is not None:
+            torch.cuda.current_stream(self.p.device).wait_event(reduced)
         d = self._adam_desc(prefix, 0, self.p, self.g, 1 if zero_end is None else 2, 0 if zero_end is None else zero_end)
         for k in ("seg_end", "lr0", "lr1", "inner", "period"):
             d[k] = d[k][:-1]
         self._kernel(d)
-        if gathered is not None:
-            torch.cuda.current_stream(self.p.device).wait_event(gathered)
+
+    def _adam_sh(self, sh):
+        ex = sh["exchange"]
         gsh = self.groups[-1]
         f = gsh["param"]
         off = self.ends[-2]
