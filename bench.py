@@ -701,7 +701,7 @@ def main():
         torch.cuda.current_stream(dev).wait_event(ready[b])
         c = cams[ci]
         cb = cam_bufs[b]
-        cam = Camera(c.image_width, c.image_height, c.FoVx, c.FoVy, cb[:16].view(4, 4), cb[16:32].view(4, 4), cb[32:35])
+        cam = Camera(c.image_width, c.image_height, c.FoVx, c.FoVy, cb[:16].view(4, 4), cb[16:32].view(4, 4), cb[32:35], uid=("view", ci))
         if e2e_mode["u8"]:
             io_image.to_device_float(gt_u8_bufs[b].view(H, W, 3), out=gt_bufs[b], hwc=True)
         trainer.step(cam, gt_bufs[b], loss_host=loss_host, loss_ready=loss_ready)

@@ -35,6 +35,7 @@ class Camera:
     world_view_transform: torch.Tensor  # [4,4], transposed W2C
     full_proj_transform: torch.Tensor   # [4,4]
     camera_center: torch.Tensor         # [3]
+    uid: object = None                  # view identity (scene/cameras.py:20 `uid`): keys the per-view statistics of NativeFrame
 
     @property
     def tanfovx(self) -> float:
@@ -47,7 +48,7 @@ class Camera:
     def to(self, device) -> "Camera":
         return Camera(self.image_width, self.image_height, self.FoVx, self.FoVy,
                       self.world_view_transform.to(device), self.full_proj_transform.to(device),
-                      self.camera_center.to(device))
+                      self.camera_center.to(device), self.uid)
 
 
 def projection_matrix(znear: float, zfar: float, fovx: float, fovy: float) -> torch.Tensor:

@@ -11,6 +11,8 @@ All gradients live in ONE contiguous buffer (param.grad are views into it), so t
 """
 from __future__ import annotations
 
+import collections
+
 import math
 from typing import List, Optional, Sequence
 
@@ -53,10 +55,15 @@ class NativeFrame:
     buffers served through the allocation callback.
 
     sync_free (default): only the FIRST frame learns N through the stock-style 4-byte read-back; from then on the binning
-    region is capacity-sized (grow-only, 1.5x the largest N seen + slack), N stays on the device and is mirrored by the
-    binning kernel into mapped pinned host memory (`n_host`: N, overflow flag) that the host polls WITHOUT synchronising.
-    A frame whose N exceeds the capacity renders the background with zero gradients and raises the flag; the next run()
-    grows the region, counts the event in `overflows` and carries on."""
+    region is capacity-sized, N stays on the device and is mirrored by the range kernel into a ring of mapped pinned host
+    slots (`n_host`: one (N, overflow flag) pair per in-flight frame) that the host polls WITHOUT synchronising.
+    The tile sort runs over the capacity, so the capacity is predicted PER VIEW: 1.08x the N this camera had at its last
+    visit (more when it moved a lot between its last two visits) + 64k; a camera seen for the first time gets 1.25x the
+    largest N seen so far + 256k.  A frame whose N exceeds its capacity renders the background with zero gradients; the
+    host notices when it harvests that frame's slot, counts it in `overflows`, and the camera's next visit is sized from
+    the true N."""
+
+    RING = 64       # mapped (N, flag) slots = frames the host may run ahead of the device before it waits
 
     def __init__(self, model: MeshGaussianModel, width: int, height: int, lambda_dssim: float = 0.2, sync_free: bool = True,
                  world: int = 1, rank: int = 0):
@@ -71,8 +78,13 @@ class NativeFrame:
         self.loss = torch.zeros(3, dtype=torch.float32, device=dev)
         self.n_rendered = C.c_int64(0)
         self.sync_free = bool(sync_free)
-        self.capacity = 0                       # duplicates the binning region is sized for (0: not known yet)
-        self.n_host = torch.zeros(2, dtype=torch.int32).pin_memory()     # written by k_bin_tiles: N, overflow flag
+        self.capacity = 0                       # duplicates the most recent frame's binning region was sized for (0: not known yet)
+        self.capacity_override = None           # tests: force the next frames' capacity
+        self.n_host = torch.zeros(self.RING, 2, dtype=torch.int32).pin_memory()   # slot i: (N, overflow flag) of an in-flight frame
+        self._n_np = self.n_host.numpy()
+        self._pending = collections.deque()     # (slot, view key, capacity) of frames whose N has not been harvested yet
+        self._view_n = {}                       # view key -> (N at the last visit, N at the visit before)
+        self._n_max, self._n_last, self._frame_no = 0, 0, 0
         self.overflows = 0
         # factored SH gradient (run(..., factored=True)): slot r of `exchange` = [3P colour gradients | camera centre | pad] of
         # rank r's frame; this rank's frame writes slot `rank`, FlatAdam(sh_factored=True) all-gathers and consumes the rest
@@ -114,8 +126,38 @@ class NativeFrame:
 
     @property
     def last_num_rendered(self) -> int:
-        """N of the most recent frame whose binning kernel has run (no synchronisation: may lag by a frame)."""
-        return int(self.n_host[0]) if (self.sync_free and self.capacity > 0) else int(self.n_rendered.value)
+        """N of the most recent frame whose range kernel has run (no synchronisation: may lag behind the queue)."""
+        if self.sync_free and self.capacity > 0:
+            self._harvest()
+            return self._n_last
+        return int(self.n_rendered.value)
+
+    def _harvest(self) -> None:
+        """Collect (N, overflow) of the frames the device has finished binning; their slots become reusable."""
+        while self._pending:
+            slot, key, cap = self._pending[0]
+            n = int(self._n_np[slot, 0])
+            if n < 0:                       # that frame's k_tile_ranges has not run yet
+                break
+            self._pending.popleft()
+            self._note(key, n)
+            if n > cap:
+                self.overflows += 1
+
+    def _note(self, key, n: int) -> None:
+        prev = self._view_n.get(key)
+        self._view_n[key] = (n, prev[0] if prev else 0)
+        self._n_max, self._n_last = max(self._n_max, n), n
+
+    def _predict_capacity(self, key) -> int:
+        if self.capacity_override is not None:
+            return int(self.capacity_override)
+        known = self._view_n.get(key)
+        if known is None:
+            return int(self._n_max * 1.25) + (1 << 18)
+        n1, n0 = known
+        drift = abs(n1 - n0) / max(n1, 1) if n0 else 0.0
+        return int(n1 * (1.0 + max(0.08, 3.0 * drift))) + (1 << 16)
 
     def sh_factors(self) -> dict:
         """What FlatAdam.step(sh=...) needs after a factored frame."""
@@ -160,20 +202,28 @@ class NativeFrame:
         a.gt, a.lambda_dssim, a.loss = gt.data_ptr(), self.lam, self.loss.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
         a.num_rendered = C.pointer(self.n_rendered)
+        key = getattr(cam, "uid", None)
+        if key is None:
+            key = id(cam)
         first = self.capacity == 0
         if self.sync_free and not first:
-            if int(self.n_host[1]) != 0:       # some earlier frame overflowed the binning region: grow before this one
-                self.overflows += 1
-                self.capacity = int(max(self.capacity, int(self.n_host[0])) * 1.25) + (1 << 18)
-                self.n_host[1] = 0
-            a.binning_capacity, a.n_host_mapped = self.capacity, self.n_host.data_ptr()
+            self._harvest()
+            if len(self._pending) >= self.RING - 1:         # the host is a whole ring ahead of the device: wait for the oldest frames
+                torch.cuda.current_stream(self.dev).synchronize()
+                self._harvest()
+            slot = self._frame_no % self.RING
+            self._frame_no += 1
+            self.capacity = self._predict_capacity(key)
+            self._n_np[slot, 0], self._n_np[slot, 1] = -1, 0
+            self._pending.append((slot, key, self.capacity))
+            a.binning_capacity, a.n_host_mapped = self.capacity, self.n_host.data_ptr() + 8 * slot
         with torch.cuda.device(self.dev):
             _lib.check(_lib.lib().gms_train_frame(C.byref(a), self._cb, None, torch.cuda.current_stream(self.dev).cuda_stream),
                        "gms_train_frame")
         if self.sync_free and first:           # the one synchronising frame told us N
             n = max(int(self.n_rendered.value), 0)
-            self.capacity = int(n * 1.25) + (1 << 18)      # the tile sort runs over the capacity: keep the slack modest
-            self.n_host[0] = n
+            self._note(key, n)
+            self.capacity = n
         return self.loss[0]
 
 

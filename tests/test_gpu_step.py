@@ -191,11 +191,17 @@ def test_sync_free_native_frame_equals_synchronising_frame():
     torch.testing.assert_close(la, lb, rtol=1e-5, atol=0)        # (the fp32 atomics of the backward make runs differ in the last bits)
     np.testing.assert_allclose(pa.numpy(), pb.numpy(), rtol=1e-3, atol=2e-4)    # Adam's first steps amplify the atomics' last-bit noise
     # forced overflow: capacity below N -> flag, background frame, then automatic growth
-    fa.capacity = max(na) // 3
-    fa.run(cams[0], gts[0], bg); torch.cuda.synchronize()
-    assert int(fa.n_host[1]) == 1
-    fa.run(cams[0], gts[0], bg); torch.cuda.synchronize()
-    assert fa.overflows == 1 and int(fa.n_host[1]) == 0 and fa.capacity >= fa.last_num_rendered > 0
+    # per-view capacity: the second visit of a camera is sized from its own N, not from the largest N seen
+    assert fa.capacity <= int(1.3 * max(na)) + (1 << 16)
+    # forced overflow: capacity below N -> background frame with zero gradients, noticed when the slot is harvested; the
+    # camera's next visit is sized from the true N
+    fa.capacity_override = max(na) // 3
+    loss_over = fa.run(cams[0], gts[0], bg).item(); torch.cuda.synchronize()
+    assert fa.last_num_rendered > fa.capacity and fa.overflows == 1
+    assert all(float(g.abs().max()) == 0.0 for g in (fa.model._alpha.grad, fa.model._scale.grad, fa.model._opacity.grad))
+    fa.capacity_override = None
+    loss_ok = fa.run(cams[0], gts[0], bg).item(); torch.cuda.synchronize()
+    assert fa.overflows == 1 and fa.capacity >= fa.last_num_rendered > 0 and loss_ok < loss_over
     assert abs(fa.last_num_rendered - na[0]) <= 0.05 * na[0]        # (same camera; the parameters moved by seven Adam steps)
 
 
