@@ -1,5 +1,6 @@
 """-m gpu: the training-step glue kernels (fused L1+SSIM loss, FlatAdam) against their PyTorch fp32 references, and the
 fast trainer against the reference-ordered op sequence."""
+import math
 import os
 
 import numpy as np
@@ -203,6 +204,66 @@ def test_sync_free_native_frame_equals_synchronising_frame():
     loss_ok = fa.run(cams[0], gts[0], bg).item(); torch.cuda.synchronize()
     assert fa.overflows == 1 and fa.capacity >= fa.last_num_rendered > 0 and loss_ok < loss_over
     assert abs(fa.last_num_rendered - na[0]) <= 0.05 * na[0]        # (same camera; the parameters moved by seven Adam steps)
+
+
+def test_adam_sh_factored_abi_survives_denormal_second_moments():
+    """gms_adam_sh_factored through the raw C ABI with colour gradients from 1e-25 (their squares underflow to denormals /
+    zero in fp32) to 1e-2 and exact zeros, degree 0 (gradient of coefficient 0 = 0.2820948 * colour gradient, the other 15
+    rows zero): finite everywhere and equal to torch.optim.Adam (fp32, eps 1e-15 as gaussian_mesh_model.py:183) over three steps."""
+    import ctypes as C
+    from gms_b200 import _lib
+    P, M = 4099, 16
+    gen = torch.Generator().manual_seed(5)
+    mag = 10.0 ** (torch.rand(P, 3, generator=gen) * 23.0 - 25.0)
+    gcol = (mag * torch.sign(torch.randn(P, 3, generator=gen))).float()
+    gcol[::7] = 0.0
+    xyz = torch.randn(P, 3, generator=gen).float().cuda()
+    slot = (3 * P + 3 + 63) // 64 * 64
+    ex = torch.zeros(1, slot, device="cuda")
+    ex[0, :3 * P] = gcol.reshape(-1).cuda()
+    ex[0, 3 * P:3 * P + 3] = torch.tensor([0.3, -2.0, 4.0])
+    p0 = torch.randn(P, M, 3, generator=gen).float()
+    p = p0.clone().cuda(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    lr_dc, lr_rest, b1, b2, eps = 2.5e-3, 1.25e-4, 0.9, 0.999, 1e-15
+    r_dc = p0[:, :1, :].clone().cuda().requires_grad_(True); r_rest = p0[:, 1:, :].clone().cuda().requires_grad_(True)
+    ref = torch.optim.Adam([{"params": [r_dc], "lr": lr_dc}, {"params": [r_rest], "lr": lr_rest}], lr=0.0, betas=(b1, b2), eps=eps)
+    g_dc = (gcol.cuda() * np.float32(0.28209479177387814)).reshape(P, 1, 3)
+    for step in (1, 2, 3):
+        a = _lib.AdamShArgs()
+        a.P, a.M, a.sh_degree, a.R = P, M, 0, 1
+        a.xyz, a.exchange, a.slot_floats, a.grad_scale = xyz.data_ptr(), ex.data_ptr(), slot, 1.0
+        a.p, a.m, a.v = p.data_ptr(), m.data_ptr(), v.data_ptr()
+        a.lr_dc, a.lr_rest, a.beta1, a.beta2, a.eps, a.step = lr_dc, lr_rest, b1, b2, eps, step
+        _lib.check(_lib.lib().gms_adam_sh_factored(C.byref(a), torch.cuda.current_stream().cuda_stream), "gms_adam_sh_factored")
+        r_dc.grad = g_dc.clone(); r_rest.grad = torch.zeros_like(r_rest)
+        ref.step()
+    torch.cuda.synchronize()
+    for t_ in (p, m, v):
+        assert torch.isfinite(t_).all()
+    # the branch-free division / square root are the compiler's own fast-path sequences: bit-identical to sqrtf and `/`
+    p2 = p0.clone().cuda(); m2 = torch.zeros_like(p2); v2 = torch.zeros_like(p2)
+    old = _lib.set_option("adam_sh_ieee", 1)
+    try:
+        for step in (1, 2, 3):
+            a = _lib.AdamShArgs()
+            a.P, a.M, a.sh_degree, a.R = P, M, 0, 1
+            a.xyz, a.exchange, a.slot_floats, a.grad_scale = xyz.data_ptr(), ex.data_ptr(), slot, 1.0
+            a.p, a.m, a.v = p2.data_ptr(), m2.data_ptr(), v2.data_ptr()
+            a.lr_dc, a.lr_rest, a.beta1, a.beta2, a.eps, a.step = lr_dc, lr_rest, b1, b2, eps, step
+            _lib.check(_lib.lib().gms_adam_sh_factored(C.byref(a), torch.cuda.current_stream().cuda_stream), "gms_adam_sh_factored")
+    finally:
+        _lib.set_option("adam_sh_ieee", old)
+    torch.cuda.synchronize()
+    nd = int((p != p2).sum()), int((m != m2).sum()), int((v != v2).sum())
+    print(f"[adam_sh] elements differing from the sqrtf / division build after 3 steps: p {nd[0]}, m {nd[1]}, v {nd[2]} of {p.numel()}; "
+          f"max |dp| {float((p - p2).abs().max()):.3e}")
+    assert nd[1] == 0 and nd[2] == 0 and float((p - p2).abs().max()) <= 2.4e-7
+    err = float((p[:, :1, :] - r_dc.detach()).abs().max())
+    assert err <= 5e-7, err                                         # (|p| ~ 1..4: a couple of ulps; the update itself is ~2.5e-3 per step)
+    assert torch.equal(p.cpu()[:, 1:, :], p0[:, 1:, :])            # rows above the active degree: zero gradient, untouched
+    moved = (p[:, 0, :].cpu() - p0[:, 0, :]).abs()
+    big = gcol.abs() > 1e-12
+    assert float(moved[big].min()) > 1e-3 and float(moved[gcol == 0].max()) == 0.0
 
 
 def test_factored_sh_gradient_equals_dense_path():
