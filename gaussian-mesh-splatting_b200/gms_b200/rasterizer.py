@@ -61,6 +61,9 @@ last_num_rendered = 0   # N of the most recent forward (statistics for bench.py)
 # When True and `shs` is a leaf whose .grad is a preallocated, zeroed, contiguous buffer (FlatAdam's contract), the
 # backward kernel writes dL/dshs (192 B/Gaussian, the largest gradient) straight into it and autograd gets None:
 # saves the AccumulateGrad read-modify-write over 3 x 192 MB per frame.  Off by default (plain autograd semantics).
+# NOT compatible with gradient accumulation: the kernel OVERWRITES the buffer (every row, also those of culled Gaussians),
+# it does not add to it -- a second backward before the optimizer step replaces the first one's SH gradient.  Callers that
+# accumulate over several frames must leave this off (the default) or use one optimizer step per frame, as train.py does.
 DIRECT_SH_GRAD = False
 
 
