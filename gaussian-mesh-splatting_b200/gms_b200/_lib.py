@@ -109,7 +109,7 @@ class FrameArgs(C.Structure):
                 ("settings", RasterSettings), ("gt", C.c_void_p), ("lambda_dssim", C.c_float), ("loss", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("num_rendered", C.POINTER(C.c_int64)),
                 ("binning_capacity", C.c_int64), ("n_host_mapped", C.c_void_p), ("d_color_sh", C.c_void_p),
-                ("event_sh_ready", C.c_void_p)]
+                ("event_sh_ready", C.c_void_p), ("event_loss_ready", C.c_void_p)]
 
 
 class FrameView(C.Structure):

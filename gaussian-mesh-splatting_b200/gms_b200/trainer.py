@@ -91,6 +91,8 @@ class NativeFrame:
         self.world, self.rank = int(world), int(rank)
         self.slot = (3 * P + 3 + 63) // 64 * 64
         self.exchange = None
+        self.ev_loss = None         # recorded by gms_train_frame right after the loss kernels (read_loss_async)
+        self._loss_read, self._side = None, None
         self.ev_sh = None           # recorded by gms_train_frame right after the preprocess backward (world > 1: the exchange of the
                                     # colour gradients starts there, on the optimizer's communication stream)
         self._check_model()
@@ -159,6 +161,20 @@ class NativeFrame:
         drift = abs(n1 - n0) / max(n1, 1) if n0 else 0.0
         return int(n1 * (1.0 + max(0.08, 3.0 * drift))) + (1 << 16)
 
+    def read_loss_async(self, loss_host: torch.Tensor, loss_ready: Optional[torch.cuda.Event] = None) -> None:
+        """Copy the last frame's loss into pinned host memory from a side stream as soon as the LOSS kernels are done (the
+        event gms_train_frame records ~40 % into the frame), not after the whole frame: a caller that waits for `loss_ready`
+        gets the value while the backward pass is still running and has that time to queue its next step."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        self._side.wait_event(self.ev_loss)
+        with torch.cuda.stream(self._side):
+            loss_host.copy_(self.loss[:1].reshape(loss_host.shape), non_blocking=True)
+            if loss_ready is not None:
+                loss_ready.record(self._side)
+            self._loss_read = torch.cuda.Event()
+            self._loss_read.record(self._side)
+
     def sh_factors(self) -> dict:
         """What FlatAdam.step(sh=...) needs after a factored frame."""
         import ctypes as C
@@ -194,6 +210,13 @@ class NativeFrame:
                     self.ev_sh = torch.cuda.Event()
                     self.ev_sh.record(torch.cuda.current_stream(self.dev))      # (creates the underlying cudaEvent_t)
                 a.event_sh_ready = self.ev_sh.cuda_event
+        if self.ev_loss is None:
+            self.ev_loss = torch.cuda.Event()
+            self.ev_loss.record(torch.cuda.current_stream(self.dev))            # (creates the underlying cudaEvent_t)
+        a.event_loss_ready = self.ev_loss.cuda_event
+        if self._loss_read is not None:         # an asynchronous read-back of the previous frame's loss (read_loss_async) must be
+            torch.cuda.current_stream(self.dev).wait_event(self._loss_read)     # done before this frame's loss kernels overwrite it
+            self._loss_read = None
         s = a.settings
         s.image_height, s.image_width, s.tanfovx, s.tanfovy = self.H, self.W, cam.tanfovx, cam.tanfovy
         s.bg, s.scale_modifier = bg.data_ptr(), 1.0
@@ -272,9 +295,10 @@ class MeshTrainer:
 
     def step(self, cam: Camera, gt: torch.Tensor, loss_host: Optional[torch.Tensor] = None,
              loss_ready: Optional[torch.cuda.Event] = None) -> torch.Tensor:
-        """One optimisation step.  If `loss_host` (pinned) / `loss_ready` are given, the loss is copied to the host right
-        after the backward pass and `loss_ready` is recorded BEFORE the optimizer kernels are queued: a caller that logs
-        the loss every step waits only for the frame, and its next step's launch overhead overlaps the Adam pass."""
+        """One optimisation step.  If `loss_host` (pinned) / `loss_ready` are given, the loss is copied to the host from a side
+        stream as soon as the loss kernels have run (native frames: NativeFrame.read_loss_async; otherwise right after the
+        backward pass, before the optimizer kernels are queued): a caller that logs the loss every step gets it while the
+        backward pass is still running and queues its next step in that time."""
         if self.native:
             if self._frame is None:
                 self._frame = NativeFrame(self.model, cam.image_width, cam.image_height, self.lambda_dssim, sync_free=self.sync_free,
@@ -284,9 +308,7 @@ class MeshTrainer:
             from . import rasterizer as _r
             _r.last_num_rendered = self._frame.last_num_rendered
             if loss_host is not None:
-                loss_host.copy_(loss.reshape(loss_host.shape), non_blocking=True)
-                if loss_ready is not None:
-                    loss_ready.record(torch.cuda.current_stream(loss.device))
+                self._frame.read_loss_async(loss_host, loss_ready)
             self._all_reduce()
             # gms_train_frame overwrites every gradient except the atomically accumulated vertex segment (group 0)
             if self.optimizer_step:

@@ -317,6 +317,9 @@ typedef struct gms_frame_args {
     void* event_sh_ready;       /* optional cudaEvent_t recorded right after the preprocess backward: d_color_sh (or d_features) is
                                    final from there on, so a data-parallel caller can start exchanging it on another stream while the
                                    opacity / expansion backward still runs */
+    void* event_loss_ready;     /* optional cudaEvent_t recorded right after the loss kernels (about 40 % into the frame): a caller that
+                                   logs the loss every step copies it to the host from another stream and can queue the next
+                                   frame while this one's backward pass still runs */
 } gms_frame_args;
 size_t gms_frame_workspace_bytes(int32_t P, int32_t W, int32_t H);
 /* Device pointers into a frame workspace (valid after gms_train_frame): this step's expansion outputs and images. */
