@@ -85,15 +85,20 @@ struct GmsWarpSlab {          // one per warp, two for the forward's double buff
 };
 
 // ------------------------------------------------------------------------------------------- tile order
-// Longest list first: counting sort of the T tiles into 32 buckets by bit-length of their list (one CTA).
+// Longest list first: counting sort of the T tiles into 33 buckets by bit-length of their list (one CTA).  Most tiles fall into
+// four or five buckets, so the shared-memory atomics are aggregated per warp: lanes with the same bucket elect a leader that
+// adds their count once (match.any), the others take their rank from the peer mask.
 __global__ void __launch_bounds__(1024) k_tile_order(int T, const int2* __restrict__ ranges, int* __restrict__ order) {
     __shared__ int s_cnt[33];
     __shared__ int s_off[33];
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x < 33) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         const int n = ranges[t].y - ranges[t].x;
-        atomicAdd(&s_cnt[n > 0 ? 32 - __clz(n) : 0], 1);
+        const int b = n > 0 ? 32 - __clz(n) : 0;
+        const unsigned peers = __match_any_sync(__activemask(), b);
+        if (lane == __ffs(peers) - 1) atomicAdd(&s_cnt[b], __popc(peers));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -103,8 +108,13 @@ __global__ void __launch_bounds__(1024) k_tile_order(int T, const int2* __restri
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         const int n = ranges[t].y - ranges[t].x;
-        const int pos = atomicAdd(&s_off[n > 0 ? 32 - __clz(n) : 0], 1);
-        order[pos] = t;
+        const int b = n > 0 ? 32 - __clz(n) : 0;
+        const unsigned peers = __match_any_sync(__activemask(), b);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&s_off[b], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        order[base + __popc(peers & ((1u << lane) - 1u))] = t;
     }
 }
 

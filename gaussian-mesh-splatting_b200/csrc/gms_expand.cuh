@@ -21,7 +21,7 @@ struct GmsFrame {
     float s[3];                  // (eps, s1, s2)
 };
 
-GMS_HD float gms_norm3(const float* v) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+GMS_HD float gms_norm3(const float* v) { return GMS_SQRTN(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 GMS_HD float gms_dotv(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
 // t = [t0 | t1 | t2] (9 floats)
@@ -29,18 +29,18 @@ GMS_HD void gms_face_frame(const float* t, float eps, GmsFrame& f) {
     const float* t0 = t; const float* t1 = t + 3; const float* t2 = t + 6;
     float e1[3], e2[3], m[3];
 #pragma unroll
-    for (int i = 0; i < 3; i++) { e1[i] = t1[i] - t0[i]; e2[i] = t2[i] - t0[i]; m[i] = (t0[i] + t1[i] + t2[i]) / 3.0f; }
+    for (int i = 0; i < 3; i++) { e1[i] = t1[i] - t0[i]; e2[i] = t2[i] - t0[i]; m[i] = GMS_DIVN(t0[i] + t1[i] + t2[i], 3.0f); }
     f.n[0] = e1[1] * e2[2] - e1[2] * e2[1];
     f.n[1] = e1[2] * e2[0] - e1[0] * e2[2];
     f.n[2] = e1[0] * e2[1] - e1[1] * e2[0];
     f.nn = gms_norm3(f.n);
-    const float inn = 1.0f / (f.nn + eps);
+    const float inn = GMS_DIVN(1.0f, f.nn + eps);
 #pragma unroll
     for (int i = 0; i < 3; i++) { f.v0[i] = f.n[i] * inn; f.a1[i] = t1[i] - m[i]; f.a2[i] = t2[i] - m[i]; }
     f.na1 = gms_norm3(f.a1);
     const float l1 = f.na1 + eps;
 #pragma unroll
-    for (int i = 0; i < 3; i++) f.v1[i] = f.a1[i] / l1;
+    for (int i = 0; i < 3; i++) f.v1[i] = GMS_DIVN(f.a1[i], l1);
     f.d0 = gms_dotv(f.a2, f.v0);
     f.d1 = gms_dotv(f.a2, f.v1);
 #pragma unroll
@@ -48,7 +48,7 @@ GMS_HD void gms_face_frame(const float* t, float eps, GmsFrame& f) {
     f.nu = gms_norm3(f.u);
     const float lu = f.nu + eps;
 #pragma unroll
-    for (int i = 0; i < 3; i++) f.v2[i] = f.u[i] / lu;
+    for (int i = 0; i < 3; i++) f.v2[i] = GMS_DIVN(f.u[i], lu);
     f.s[0] = eps;
     f.s[1] = l1 / 2.0f;
     f.s[2] = gms_dotv(f.a2, f.v2) / 2.0f;
@@ -64,7 +64,7 @@ GMS_HD void gms_frame_quat(const GmsFrame& f, float* q, GmsQuatAux& ax) {
     float x[4] = {1.0f + m00 + m11 + m22, 1.0f + m00 - m11 - m22, 1.0f - m00 + m11 - m22, 1.0f - m00 - m11 + m22};
     float qa[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) qa[i] = x[i] > 0.f ? sqrtf(x[i]) : 0.f;
+    for (int i = 0; i < 4; i++) qa[i] = x[i] > 0.f ? GMS_SQRTN(x[i]) : 0.f;
     int sel = 0;
 #pragma unroll
     for (int i = 1; i < 4; i++) if (qa[i] > qa[sel]) sel = i;   // first maximum, like torch.argmax
@@ -77,7 +77,7 @@ GMS_HD void gms_frame_quat(const GmsFrame& f, float* q, GmsQuatAux& ax) {
     const float D = 2.0f * fmaxf(qa[sel], 0.1f);
     float o[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) o[i] = c[i] / D;
+    for (int i = 0; i < 4; i++) o[i] = GMS_DIVN(c[i], D);        // D >= 0.2
     const float sgn = o[0] < 0.f ? -1.f : 1.f;
 #pragma unroll
     for (int i = 0; i < 4; i++) { q[i] = sgn * o[i]; ax.cand[i] = c[i]; }
@@ -88,12 +88,12 @@ GMS_HD void gms_frame_quat(const GmsFrame& f, float* q, GmsQuatAux& ax) {
 GMS_HD void gms_frame_quat_backward(const GmsQuatAux& ax, const float* dq, float* dv0, float* dv1, float* dv2) {
     float dc[4]; float dD = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { dc[i] = ax.sgn * dq[i] / ax.D; dD -= ax.sgn * dq[i] * ax.cand[i] / (ax.D * ax.D); }
+    for (int i = 0; i < 4; i++) { dc[i] = GMS_DIVN(ax.sgn * dq[i], ax.D); dD -= GMS_DIVN(ax.sgn * dq[i] * ax.cand[i], ax.D * ax.D); }
     // d x_sel : cand[sel] = qa^2 = x (x > 0) ; D = 2*max(qa, 0.1)
     float dx = 0.f;
     if (ax.qa > 0.f) {
         dx = dc[ax.sel];
-        if (ax.qa > 0.1f) dx += dD / ax.qa;        // dD * dD/dqa * dqa/dx = dD * 2 * 1/(2 qa)
+        if (ax.qa > 0.1f) dx += GMS_DIVN(dD, ax.qa);        // dD * dD/dqa * dqa/dx = dD * 2 * 1/(2 qa)
     }
     float dm[9];
 #pragma unroll
@@ -140,7 +140,7 @@ GMS_HD void gms_face_frame_backward(const float* t, float eps, const GmsFrame& f
     {
         const float k = f.nu > 0.f ? gms_dotv(dv2, f.u) / (f.nu * lu * lu) : 0.f;
 #pragma unroll
-        for (int i = 0; i < 3; i++) du[i] = dv2[i] / lu - k * f.u[i];
+        for (int i = 0; i < 3; i++) du[i] = GMS_DIVN(dv2[i], lu) - k * f.u[i];
     }
     // u = a2 - (a2.v0) v0 - (a2.v1) v1
     {
@@ -155,15 +155,15 @@ GMS_HD void gms_face_frame_backward(const float* t, float eps, const GmsFrame& f
     // v1 = a1 / l1 ; l1 = |a1| + eps ; s1 = l1 / 2
     {
         const float l1 = f.na1 + eps;
-        const float dl1 = 0.5f * ds1 - gms_dotv(dv1, f.a1) / (l1 * l1);
+        const float dl1 = 0.5f * ds1 - GMS_DIVN(gms_dotv(dv1, f.a1), l1 * l1);      // l1 >= eps: l1^2 >= 1e-16
         const float k = f.na1 > 0.f ? dl1 / f.na1 : 0.f;
 #pragma unroll
-        for (int i = 0; i < 3; i++) da1[i] += dv1[i] / l1 + k * f.a1[i];
+        for (int i = 0; i < 3; i++) da1[i] += GMS_DIVN(dv1[i], l1) + k * f.a1[i];
     }
     // a1 = t1 - m ; a2 = t2 - m ; m = (t0+t1+t2)/3
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const float dm = -(da1[i] + da2[i]) / 3.0f;
+        const float dm = GMS_DIVN(-(da1[i] + da2[i]), 3.0f);
         dt[i] += dm; dt[3 + i] += da1[i] + dm; dt[6 + i] += da2[i] + dm;
     }
     // v0 = n / (|n| + eps) ; n = e1 x e2
@@ -172,7 +172,7 @@ GMS_HD void gms_face_frame_backward(const float* t, float eps, const GmsFrame& f
         const float k = f.nn > 0.f ? gms_dotv(dv0, f.n) / (f.nn * ln * ln) : 0.f;
         float dn[3], e1[3], e2[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) { dn[i] = dv0[i] / ln - k * f.n[i]; e1[i] = t1[i] - t0[i]; e2[i] = t2[i] - t0[i]; }
+        for (int i = 0; i < 3; i++) { dn[i] = GMS_DIVN(dv0[i], ln) - k * f.n[i]; e1[i] = t1[i] - t0[i]; e2[i] = t2[i] - t0[i]; }
         const float de1[3] = {e2[1] * dn[2] - e2[2] * dn[1], e2[2] * dn[0] - e2[0] * dn[2], e2[0] * dn[1] - e2[1] * dn[0]};
         const float de2[3] = {dn[1] * e1[2] - dn[2] * e1[1], dn[2] * e1[0] - dn[0] * e1[2], dn[0] * e1[1] - dn[1] * e1[0]};
 #pragma unroll
@@ -211,13 +211,13 @@ GMS_HD void gms_expand_face_fwd(const gms_expand_args& a, int f, int fl) {
     float q[4];
     GmsQuatAux ax;
     gms_frame_quat(fr, q, ax);
-    const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+    const float qn = fmaxf(GMS_SQRTN(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
     for (int k = 0; k < a.K; k++) {
         const size_t p = (size_t)fl * a.K + k;
         const float r0 = fmaxf(a.alpha_raw[3 * p], 0.f) + 1e-8f, r1 = fmaxf(a.alpha_raw[3 * p + 1], 0.f) + 1e-8f,
                     r2 = fmaxf(a.alpha_raw[3 * p + 2], 0.f) + 1e-8f;
         const float S = r0 + r1 + r2;
-        const float al0 = r0 / S, al1 = r1 / S, al2 = r2 / S;
+        const float al0 = GMS_DIVN(r0, S), al1 = GMS_DIVN(r1, S), al2 = GMS_DIVN(r2, S);        // S >= 3e-8
         if (a.alpha) { a.alpha[3 * p] = al0; a.alpha[3 * p + 1] = al1; a.alpha[3 * p + 2] = al2; }
         if (a.xyz) {
 #pragma unroll
@@ -231,7 +231,7 @@ GMS_HD void gms_expand_face_fwd(const gms_expand_args& a, int f, int fl) {
             if (a.scaling_act) a.scaling_act[3 * p + c] = expf(logf(inner));
         }
         if (a.rotation_raw) { float* o = a.rotation_raw + 4 * p; o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3]; }
-        if (a.rotation_act) { float* o = a.rotation_act + 4 * p; o[0] = q[0] / qn; o[1] = q[1] / qn; o[2] = q[2] / qn; o[3] = q[3] / qn; }
+        if (a.rotation_act) { float* o = a.rotation_act + 4 * p; o[0] = GMS_DIVN(q[0], qn); o[1] = GMS_DIVN(q[1], qn); o[2] = GMS_DIVN(q[2], qn); o[3] = GMS_DIVN(q[3], qn); }
     }
 }
 
@@ -253,7 +253,7 @@ GMS_HD void gms_expand_face_bwd(const gms_expand_args& a, const gms_expand_grads
     float q[4];
     GmsQuatAux ax;
     gms_frame_quat(fr, q, ax);
-    const float qnorm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float qnorm = GMS_SQRTN(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     const float qn = fmaxf(qnorm, 1e-12f);
     float dt[9];
 #pragma unroll
@@ -268,7 +268,7 @@ GMS_HD void gms_expand_face_bwd(const gms_expand_args& a, const gms_expand_grads
         const float ar[3] = {a.alpha_raw[3 * p], a.alpha_raw[3 * p + 1], a.alpha_raw[3 * p + 2]};
         const float r[3] = {fmaxf(ar[0], 0.f) + 1e-8f, fmaxf(ar[1], 0.f) + 1e-8f, fmaxf(ar[2], 0.f) + 1e-8f};
         const float S = r[0] + r[1] + r[2];
-        const float al[3] = {r[0] / S, r[1] / S, r[2] / S};
+        const float al[3] = {GMS_DIVN(r[0], S), GMS_DIVN(r[1], S), GMS_DIVN(r[2], S)};
         float dal[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -279,7 +279,7 @@ GMS_HD void gms_expand_face_bwd(const gms_expand_args& a, const gms_expand_grads
         const float dsum = dal[0] * al[0] + dal[1] * al[1] + dal[2] * al[2];
         if (g.dL_dalpha_raw) {
 #pragma unroll
-            for (int j = 0; j < 3; j++) g.dL_dalpha_raw[3 * p + j] = ar[j] > 0.f ? (dal[j] - dsum) / S : 0.f;
+            for (int j = 0; j < 3; j++) g.dL_dalpha_raw[3 * p + j] = ar[j] > 0.f ? GMS_DIVN(dal[j] - dsum, S) : 0.f;
         }
         // --- scaling
         const float cs = a.scale_raw[p];
@@ -290,7 +290,7 @@ GMS_HD void gms_expand_face_bwd(const gms_expand_args& a, const gms_expand_grads
             const float prod = cs * fr.s[c];
             const float inner = fmaxf(prod, 0.f) + a.eps;
             if (g.dL_dscaling_act) gl += g.dL_dscaling_act[3 * p + c] * expf(logf(inner));
-            const float dprod = prod > 0.f ? gl / inner : 0.f;
+            const float dprod = prod > 0.f ? GMS_DIVN(gl, inner) : 0.f;       // inner >= eps
             dcs += dprod * fr.s[c];
             if (c == 1) ds1 += dprod * cs;
             if (c == 2) ds2 += dprod * cs;
@@ -305,12 +305,12 @@ GMS_HD void gms_expand_face_bwd(const gms_expand_args& a, const gms_expand_grads
             const float* dp = g.dL_drotation_act + 4 * p;
             const float d_x = dp[0], d_y = dp[1], d_z = dp[2], d_w = dp[3];
             if (qnorm >= 1e-12f) {
-                const float u[4] = {q[0] / qn, q[1] / qn, q[2] / qn, q[3] / qn};
+                const float u[4] = {GMS_DIVN(q[0], qn), GMS_DIVN(q[1], qn), GMS_DIVN(q[2], qn), GMS_DIVN(q[3], qn)};       // qn >= 1e-12
                 const float dd = d_x * u[0] + d_y * u[1] + d_z * u[2] + d_w * u[3];
-                dq[0] += (d_x - u[0] * dd) / qn; dq[1] += (d_y - u[1] * dd) / qn;
-                dq[2] += (d_z - u[2] * dd) / qn; dq[3] += (d_w - u[3] * dd) / qn;
+                dq[0] += GMS_DIVN(d_x - u[0] * dd, qn); dq[1] += GMS_DIVN(d_y - u[1] * dd, qn);
+                dq[2] += GMS_DIVN(d_z - u[2] * dd, qn); dq[3] += GMS_DIVN(d_w - u[3] * dd, qn);
             } else {
-                dq[0] += d_x / qn; dq[1] += d_y / qn; dq[2] += d_z / qn; dq[3] += d_w / qn;
+                dq[0] += GMS_DIVN(d_x, qn); dq[1] += GMS_DIVN(d_y, qn); dq[2] += GMS_DIVN(d_z, qn); dq[3] += GMS_DIVN(d_w, qn);
             }
         }
     }
@@ -371,8 +371,8 @@ GMS_HD void gms_points_face_fwd(const gms_points_args& a, int i) {
     }
     if (a.rotation_raw) { float* o = a.rotation_raw + 4 * (size_t)i; o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3]; }
     if (a.rotation_act) {
-        const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
-        float* o = a.rotation_act + 4 * (size_t)i; o[0] = q[0] / qn; o[1] = q[1] / qn; o[2] = q[2] / qn; o[3] = q[3] / qn;
+        const float qn = fmaxf(GMS_SQRTN(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+        float* o = a.rotation_act + 4 * (size_t)i; o[0] = GMS_DIVN(q[0], qn); o[1] = GMS_DIVN(q[1], qn); o[2] = GMS_DIVN(q[2], qn); o[3] = GMS_DIVN(q[3], qn);
     }
 }
 
