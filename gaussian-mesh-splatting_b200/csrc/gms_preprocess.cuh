@@ -55,17 +55,17 @@ GMS_HD void gms_cov2d(const float* pview, const float* cov6, const float* view, 
                       float tanfovx, float tanfovy, GmsCov2D& o) {
     const float tz = pview[2];
     const float limx = GMS_MUL(1.3f, tanfovx), limy = GMS_MUL(1.3f, tanfovy);
-    const float txtz = GMS_DIV(pview[0], tz), tytz = GMS_DIV(pview[1], tz);
+    const float txtz = GMS_DIVP(pview[0], tz), tytz = GMS_DIVP(pview[1], tz);
     o.xmul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
     o.ymul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
     const float tx = GMS_MUL(fminf(limx, fmaxf(-limx, txtz)), tz);
     const float ty = GMS_MUL(fminf(limy, fmaxf(-limy, tytz)), tz);
     o.tx = tx; o.ty = ty; o.tz = tz;
     const float tz2 = GMS_MUL(tz, tz);
-    const float J00 = GMS_DIV(focal_x, tz);
-    const float J02 = GMS_DIV(-GMS_MUL(focal_x, tx), tz2);
-    const float J11 = GMS_DIV(focal_y, tz);
-    const float J12 = GMS_DIV(-GMS_MUL(focal_y, ty), tz2);
+    const float J00 = GMS_DIVP(focal_x, tz);
+    const float J02 = GMS_DIVP(-GMS_MUL(focal_x, tx), tz2);
+    const float J11 = GMS_DIVP(focal_y, tz);
+    const float J12 = GMS_DIVP(-GMS_MUL(focal_y, ty), tz2);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         const float W0j = view[4 * j + 0], W1j = view[4 * j + 1], W2j = view[4 * j + 2];
@@ -128,7 +128,7 @@ GMS_HD bool gms_preprocess_geom(const float* mean, const float* scale, const flo
     if (pview[2] <= GMS_NEAR) return false;
     float phom[4];
     gms_xform4x4(proj, mean[0], mean[1], mean[2], phom);
-    const float pw = GMS_DIV(1.0f, GMS_ADD(phom[3], 0.0000001f));
+    const float pw = GMS_DIVP(1.0f, GMS_ADD(phom[3], 0.0000001f));
     const float pprojx = GMS_MUL(phom[0], pw), pprojy = GMS_MUL(phom[1], pw);
     if (cov6_in) {
 #pragma unroll
@@ -144,13 +144,13 @@ GMS_HD bool gms_preprocess_geom(const float* mean, const float* scale, const flo
     const float det = GMS_FMA(a, c, -GMS_MUL(b, b));
     if (det == 0.0f) return false;
     float h_scale = 1.0f;
-    if (antialiasing) h_scale = GMS_SQRT(fmaxf(0.000025f, GMS_DIV(det_cov, det)));
-    const float det_inv = GMS_DIV(1.f, det);
+    if (antialiasing) h_scale = GMS_SQRTP(fmaxf(0.000025f, GMS_DIVP(det_cov, det)));
+    const float det_inv = GMS_DIVP(1.f, det);
     o.conx = GMS_MUL(c, det_inv); o.cony = GMS_MUL(-b, det_inv); o.conz = GMS_MUL(a, det_inv);
     const float mid = GMS_MUL(0.5f, GMS_ADD(a, c));
-    const float disc = GMS_SQRT(fmaxf(0.1f, GMS_FMA(mid, mid, -det)));
+    const float disc = GMS_SQRTP(fmaxf(0.1f, GMS_FMA(mid, mid, -det)));
     const float lambda1 = GMS_ADD(mid, disc), lambda2 = GMS_SUB(mid, disc);
-    const int my_radius = (int)ceilf(GMS_MUL(3.f, GMS_SQRT(fmaxf(lambda1, lambda2))));
+    const int my_radius = (int)ceilf(GMS_MUL(3.f, GMS_SQRTP(fmaxf(lambda1, lambda2))));
     o.px = GMS_MUL(GMS_FMA(GMS_ADD(pprojx, 1.0f), (float)W, -1.0f), 0.5f);
     o.py = GMS_MUL(GMS_FMA(GMS_ADD(pprojy, 1.0f), (float)H, -1.0f), 0.5f);
     gms_get_rect(o.px, o.py, my_radius, gx, gy, &o.x0, &o.y0, &o.x1, &o.y1);
@@ -167,8 +167,8 @@ GMS_HD bool gms_preprocess_geom(const float* mean, const float* scale, const flo
 GMS_HD void gms_sh_color(int deg, const float* mean, const float* campos, const float* sh, float* rgb,
                          uint8_t* clamped) {
     float dx = mean[0] - campos[0], dy = mean[1] - campos[1], dz = mean[2] - campos[2];
-    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
-    dx /= len; dy /= len; dz /= len;
+    const float len = GMS_SQRTP(dx * dx + dy * dy + dz * dz);
+    dx = GMS_DIVP(dx, len); dy = GMS_DIVP(dy, len); dz = GMS_DIVP(dz, len);
     float B[16];
     gms_sh_basis(deg, dx, dy, dz, B);
     const int nc = (deg + 1) * (deg + 1);
@@ -216,12 +216,12 @@ GMS_HD void gms_preprocess_backward_geom(const float* mean, const float* scale, 
     const float det = a * c - b * b;
     float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
     if (antialiasing) {
-        const float ratio = det_cov / det;
-        const float h_scale = sqrtf(fmaxf(0.000025f, ratio));
+        const float ratio = GMS_DIVP(det_cov, det);
+        const float h_scale = GMS_SQRTP(fmaxf(0.000025f, ratio));
         go.dopacity = gi.dopac * h_scale;
         if (ratio > 0.000025f) {
-            const float dL_dratio = gi.dopac * opacity_in / (2.f * h_scale);
-            const float inv_det = 1.f / det;
+            const float dL_dratio = GMS_DIVP(gi.dopac * opacity_in, 2.f * h_scale);
+            const float inv_det = GMS_DIVP(1.f, det);
             const float k = dL_dratio * inv_det * inv_det;
             dL_da += k * (c0 * det - det_cov * c);
             dL_dc += k * (a0 * det - det_cov * a);
@@ -232,7 +232,7 @@ GMS_HD void gms_preprocess_backward_geom(const float* mean, const float* scale, 
     }
     const float dcx = gi.dconic[0], dcy = gi.dconic[1], dcz = gi.dconic[2];
     const float denom = det;
-    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    const float denom2inv = GMS_DIVP(1.0f, (denom * denom) + 0.0000001f);
     if (denom2inv != 0.f) {
         dL_da += denom2inv * (-c * c * dcx + 2.f * b * c * dcy + (denom - a * c) * dcz);
         dL_dc += denom2inv * (-a * a * dcz + 2.f * a * b * dcy + (denom - a * c) * dcx);
@@ -267,19 +267,19 @@ GMS_HD void gms_preprocess_backward_geom(const float* mean, const float* scale, 
         dJ00 += dM0[j] * W0j; dJ02 += dM0[j] * W2j;
         dJ11 += dM1[j] * W1j; dJ12 += dM1[j] * W2j;
     }
-    const float tz = 1.f / c2.tz, tz2 = tz * tz, tz3 = tz2 * tz;
+    const float tz = GMS_DIVP(1.f, c2.tz), tz2 = tz * tz, tz3 = tz2 * tz;
     const float dL_dtx = c2.xmul * -focal_x * tz2 * dJ02;
     const float dL_dty = c2.ymul * -focal_y * tz2 * dJ12;
     float dL_dtz = -focal_x * tz2 * dJ00 - focal_y * tz2 * dJ11 + (2.f * focal_x * c2.tx) * tz3 * dJ02 +
                    (2.f * focal_y * c2.ty) * tz3 * dJ12;
-    dL_dtz -= gi.dinvdepth / (pview[2] * pview[2]);
+    dL_dtz -= GMS_DIVP(gi.dinvdepth, pview[2] * pview[2]);
     float dmx = view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz;
     float dmy = view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz;
     float dmz = view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz;
 
     float phom[4];
     gms_xform4x4(proj, mean[0], mean[1], mean[2], phom);
-    const float m_w = 1.0f / (phom[3] + 0.0000001f);
+    const float m_w = GMS_DIVP(1.0f, phom[3] + 0.0000001f);
     const float mul1 = phom[0] * m_w * m_w, mul2 = phom[1] * m_w * m_w;
     const float g2x = gi.dmean2D[0], g2y = gi.dmean2D[1];
     dmx += (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
@@ -326,8 +326,8 @@ GMS_HD void gms_preprocess_backward_geom(const float* mean, const float* scale, 
 GMS_HD void gms_sh_backward(int deg, int M, const float* mean, const float* campos, const float* sh,
                             const float* dcolor, const uint8_t* clamped, float* dsh, float* dmean) {
     const float vx = mean[0] - campos[0], vy = mean[1] - campos[1], vz = mean[2] - campos[2];
-    const float len = sqrtf(vx * vx + vy * vy + vz * vz);
-    const float x = vx / len, y = vy / len, z = vz / len;
+    const float len = GMS_SQRTP(vx * vx + vy * vy + vz * vz);
+    const float x = GMS_DIVP(vx, len), y = GMS_DIVP(vy, len), z = GMS_DIVP(vz, len);
     float g[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) g[ch] = clamped[ch] ? 0.f : dcolor[ch];
@@ -367,7 +367,7 @@ GMS_HD void gms_sh_backward(int deg, int M, const float* mean, const float* camp
         }
     }
     const float dotp = x * ddx + y * ddy + z * ddz;
-    dmean[0] += (ddx - x * dotp) / len;
-    dmean[1] += (ddy - y * dotp) / len;
-    dmean[2] += (ddz - z * dotp) / len;
+    dmean[0] += GMS_DIVP(ddx - x * dotp, len);
+    dmean[1] += GMS_DIVP(ddy - y * dotp, len);
+    dmean[2] += GMS_DIVP(ddz - z * dotp, len);
 }
