@@ -109,7 +109,8 @@ typedef struct gms_raster_saved {
     int64_t num_visible;    /* Gaussians with radii > 0 (statistics; may be -1 if not computed) */
     int64_t binning_capacity; /* duplicates the binning region was sized for (== num_rendered on the synchronising call) */
     int32_t flags;          /* bit 0: counting binning layout (point list first; no key arrays); bit 1: per-quad survivor lists
-                               of the forward compositing pass follow the point list (consumed by backward) */
+                               of the forward compositing pass follow the point list (consumed by backward); bit 2: the sorted
+                               tile keys are 16-bit (tile count <= 65535) -- gms_debug_get_views then reports no key array */
 } gms_raster_saved;
 
 /* Gradients produced by backward (caller-allocated; NULL where the corresponding input was NULL). */
