@@ -85,7 +85,7 @@ ALGO_BYTES = {  # algorithmic bytes per unit, SURVEY.md section 8(d) / DESIGN.md
     "composite_bwd": dict(N=84, px=24), "composite_fwd": dict(N=44, px=24),
     "preprocess_fwd": dict(P=311 + 8), "preprocess_bwd": dict(P=563 - 192 + 12),     # factored SH gradient: 12 B colour gradient instead of 192 B of rows
     "expand_fwd": dict(P=56, F=60), "expand_bwd": dict(P=56, F=36),
-    "emit_dups": dict(P=16, N=8), "cub_sort_tiles": dict(P=2 * 12, N=4), "cub_sort_depth": dict(P=16), "tile_ranges": dict(N=4),
+    "emit_dups": dict(P=16, N=6), "cub_sort_tiles": dict(N=12), "cub_sort_depth": dict(P=16), "tile_ranges": dict(N=2),     # 16-bit tile keys + 32-bit Gaussian ids
     "cub_scan_tiles": dict(P=12), "ssim_stats": dict(px=3 * (8 + 12)), "ssim_grad": dict(px=3 * (12 + 8 + 4)),
     "adam": dict(P=5 * 28 + 48 * 24 + 12 + 12),   # 5 non-SH parameters/Gaussian at 28 B (p, g, m, v read; p, m, v written) + 48 SH parameters at
                                                   # 24 B (no gradient read: rebuilt from 12 B of colour gradient per rank and the 12 B centre)
