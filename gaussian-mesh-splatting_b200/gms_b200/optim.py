@@ -121,7 +121,6 @@ class FlatAdam:
         gathered = reduced = None
         if self.world > 1:
             dev = self.p.device
-            main = torch.cuda.current_stream(dev)
             avg = dist.get_backend() == "nccl"
 
             def reduce_rest():
@@ -135,6 +134,7 @@ class FlatAdam:
                 # preprocess backward (event recorded inside gms_train_frame) and overlaps the opacity / expansion backward; the
                 # all-reduce of the other gradients starts when the frame is complete and overlaps k_adam_sh, which needs the
                 # gather only.  k_adam (the non-SH parameters) waits for the all-reduce.
+                main = torch.cuda.current_stream(dev)
                 if self._comm is None:
                     self._comm = torch.cuda.Stream(dev)
                 comm = self._comm

@@ -129,3 +129,57 @@ def test_sharded_flat_adam_world2_equals_single_process():
         torch.testing.assert_close(out[r][0][:ref.n], ref.p, rtol=1e-6, atol=1e-7)     # every replica == the single-process optimiser
         assert torch.equal(out[r][0], out[0][0])                                         # replicas identical bit for bit
         assert float(out[r][1][:ref.ends[0]].abs().max()) == 0.0                         # the vertex-gradient segment was re-zeroed
+
+
+def _groups_features_last(seed=0):
+    g = _make_groups(seed)
+    return [g[0], g[1], g[3], g[4], g[2]]          # mesh_model_groups(features_last=True): the packed SH tensor closes the list
+
+
+def _factored_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gms_b200.optim import FlatAdam
+    opt = FlatAdam(_groups_features_last(), world=world, rank=rank, kernel=_adam_stub, sh_factored=True)
+    seen = []
+    opt._adam_sh = lambda sh: seen.append(sh["exchange"].clone())          # (the SH update itself is a CUDA kernel: -m gpu tests)
+    P, slot = 40, 192
+    ex = torch.zeros(world, slot)
+    for step in range(3):
+        cam = shard_cameras(8, step, rank, world)
+        opt.g.copy_(_frame_gradient(opt.n, cam, step))
+        ex.zero_()
+        ex[rank, :3 * P + 3] = torch.arange(3 * P + 3, dtype=torch.float32) + 1000.0 * cam      # this rank's colour gradients + camera centre
+        opt.step(zero_end=opt.ends[0], sh=dict(xyz=0, exchange=ex, degree=3, event=None))
+    out[rank] = (opt.p.clone(), opt.g.clone(), opt.n, opt.ends[-2], [t.clone() for t in seen], opt.m.numel())
+    dist.destroy_process_group()
+
+
+def test_factored_flat_adam_world2_exchange_and_replicated_update():
+    """FlatAdam(sh_factored=True) under gloo: the colour-gradient slots of BOTH ranks reach every rank before the SH update
+    is called, the other groups' gradients are averaged and updated by the (replicated) k_adam pass, the SH segment is left
+    to the factored kernel, and the moments are kept in full on every rank."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_factored_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    from gms_b200.optim import FlatAdam
+    ref = FlatAdam(_groups_features_last(), world=1, rank=0, kernel=_adam_stub, sh_factored=True)
+    ref._adam_sh = lambda sh: None
+    n, prefix = out[0][2], out[0][3]
+    assert prefix == ref.ends[-2] and out[0][5] == n                # full-length moments: replicated optimizer
+    for step in range(3):
+        cams = [shard_cameras(8, step, r, world) for r in range(world)]
+        gavg = sum(_frame_gradient(n, c, step) for c in cams) / world
+        ref.g.copy_(gavg[:ref.n])
+        ref.step(zero_end=ref.ends[0], sh=dict(xyz=0, exchange=torch.zeros(1, 192), degree=3, event=None))
+        for r in range(world):
+            got = out[r][4][step]
+            for q, c in enumerate(cams):                            # slot q holds rank q's frame on every rank
+                assert float(got[q, 0]) == 1000.0 * c + 0.0 and float(got[q, 122]) == 1000.0 * c + 122.0
+    init = _groups_features_last()[-1]["param"].detach().reshape(-1)
+    for r in range(world):
+        torch.testing.assert_close(out[r][0][:prefix], ref.p[:prefix], rtol=1e-6, atol=1e-7)
+        assert torch.equal(out[r][0], out[0][0])
+        assert torch.equal(out[r][0][prefix:prefix + init.numel()], init)      # the SH parameters were not touched by k_adam
+        assert float(out[r][1][:ref.ends[0]].abs().max()) == 0.0
