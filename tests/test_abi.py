@@ -22,6 +22,28 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert b"sm_100a" in L.gms_version()
 
 
+def test_header_is_plain_c_and_struct_sizes_match_the_ctypes_mirror(tmp_path):
+    """include/gms_b200.h is the contract a C / cgo / JNI binding compiles against: it must be valid C99 on its own, and the
+    ctypes structures of gms_b200/_lib.py (what every Python call marshals through) must have the sizes the C compiler gives
+    the header's structs."""
+    import ctypes
+    import subprocess
+    names = {"gms_raster_settings": _lib.RasterSettings, "gms_raster_inputs": _lib.RasterInputs, "gms_raster_outputs": _lib.RasterOutputs,
+             "gms_raster_saved": _lib.RasterSaved, "gms_raster_grads": _lib.RasterGrads, "gms_frame_args": _lib.FrameArgs,
+             "gms_adam_args": _lib.AdamArgs, "gms_adam_sh_args": _lib.AdamShArgs, "gms_frame_view": _lib.FrameView,
+             "gms_debug_views": _lib.DebugViews, "gms_expand_args": _lib.ExpandArgs, "gms_expand_grads": _lib.ExpandGrads,
+             "gms_points_args": _lib.PointsArgs, "gms_points_vertices_args": _lib.PointsVerticesArgs, "gms_loss_args": _lib.LossArgs}
+    src = tmp_path / "sizes.c"
+    body = "".join(f'    printf("{n} %zu\\n", sizeof({n}));\n' for n in names)
+    src.write_text('#include <stdio.h>\n#include "gms_b200.h"\nint main(void) {\n' + body + "    return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    sizes = dict((l.split()[0], int(l.split()[1])) for l in out.strip().split("\n"))
+    for n, cls in names.items():
+        assert sizes[n] == ctypes.sizeof(cls), (n, sizes[n], ctypes.sizeof(cls))
+
+
 def test_shim_module_name_and_settings_fields():
     import diff_gaussian_rasterization as d
     fields = d.GaussianRasterizationSettings._fields
