@@ -22,10 +22,10 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert b"sm_100a" in L.gms_version()
 
 
-def test_header_is_plain_c_and_struct_sizes_match_the_ctypes_mirror(tmp_path):
+def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirror(tmp_path):
     """include/gms_b200.h is the contract a C / cgo / JNI binding compiles against: it must be valid C99 on its own, and the
     ctypes structures of gms_b200/_lib.py (what every Python call marshals through) must have the sizes the C compiler gives
-    the header's structs."""
+    the header's structs, field by field."""
     import ctypes
     import subprocess
     names = {"gms_raster_settings": _lib.RasterSettings, "gms_raster_inputs": _lib.RasterInputs, "gms_raster_outputs": _lib.RasterOutputs,
@@ -35,13 +35,16 @@ def test_header_is_plain_c_and_struct_sizes_match_the_ctypes_mirror(tmp_path):
              "gms_points_args": _lib.PointsArgs, "gms_points_vertices_args": _lib.PointsVerticesArgs, "gms_loss_args": _lib.LossArgs}
     src = tmp_path / "sizes.c"
     body = "".join(f'    printf("{n} %zu\\n", sizeof({n}));\n' for n in names)
-    src.write_text('#include <stdio.h>\n#include "gms_b200.h"\nint main(void) {\n' + body + "    return 0;\n}\n")
+    body += "".join(f'    printf("{n}.{f[0]} %zu\\n", offsetof({n}, {f[0]}));\n' for n, cls in names.items() for f in cls._fields_)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gms_b200.h"\nint main(void) {\n' + body + "    return 0;\n}\n")
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)], text=True)
     sizes = dict((l.split()[0], int(l.split()[1])) for l in out.strip().split("\n"))
     for n, cls in names.items():
         assert sizes[n] == ctypes.sizeof(cls), (n, sizes[n], ctypes.sizeof(cls))
+        for f in cls._fields_:                      # same field names, same offsets (175 fields)
+            assert sizes[f"{n}.{f[0]}"] == getattr(cls, f[0]).offset, (n, f[0])
 
 
 def test_shim_module_name_and_settings_fields():
